@@ -1,0 +1,257 @@
+// polar_core.cuh -- device-side SC / SCL decoder core for sm_100a.
+//
+// Work mapping ("thread per path"): a frame is decoded by a group of MP
+// adjacent lanes (MP = list capacity rounded up to a power of two, 1..8), so a
+// warp holds FPW = 32/MP frames and never synchronises with other warps.  All
+// frames follow the same static SC schedule (the frozen pattern is a property
+// of the code, not of the frame), so the warp runs divergence-free.
+//
+// What replaces the reference's per-fork deep copies
+// (dl_scl_polar/polar/scl.py:52-62, 77 % of its run time):
+//   * LLR tree in shared memory, lane-interleaved: element (height h, index i)
+//     of slot `lane` lives at tree[(2^h-2+i)*32 + lane], so every access of a
+//     warp hits 32 distinct banks whatever slot each path points to.
+//   * Lazy copy: a path keeps one 4-bit slot pointer per tree height (word P).
+//     Because every live path recomputes heights <= c in the same phase, a
+//     path always writes its OWN slot and a fork copies one register.
+//   * Partial sums (scl.py:84-99) are bit-packed: for each height h the 2^h
+//     bits of the finished left child wait in a register field; the upward
+//     XOR propagation is a handful of shifts per decided bit.
+//   * u-hat is never stored: after the last phase the propagated word is the
+//     re-encoded codeword x^, and u^ = x^ * F^{(x)n} (F^{(x)n} is an involution).
+//
+// Reference semantics kept bit-for-bit (scl.py:108-209): both children of a
+// free bit are scored with the exact softplus metric (scl.py:102-105), the
+// list is re-sorted after EVERY phase with a stable sort whose tie order is
+// (parent rank, bit) and truncated to M.  The stable order is obtained by
+// ranking unique 64-bit keys = (IEEE bits of the fp64 metric & ~15) | (2*rank+bit).
+// Metrics accumulate in fp64; LLR arithmetic is fp32 (f exact, g one rounding).
+// Frames in which two competing metrics come within ~1e-6 relative are flagged
+// (PB_FLAG_NEAR_TIE) -- these are the only frames allowed to differ from the
+// float64 reference.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define PB_FLAG_NEAR_TIE 1u      // two competing path metrics within ~1e-6 relative at some prune
+#define PB_FLAG_RANK_TIE 2u      // DL-SCL: best and runner-up flip scores within ~1e-6 relative
+
+namespace pb {
+
+constexpr int kMaxLog = 9;            // N <= 512
+constexpr int kMaxWords = 16;         // N/32
+constexpr uint32_t kFull = 0xffffffffu;
+
+// Code description handed to every kernel by value (lives in the constant bank).
+struct Code {
+    int N, n, K, M;                   // code length, log2, info bits, list size (M <= MP)
+    int crc_deg;                      // 0 = no CRC
+    uint32_t info_mask[kMaxWords];    // bit phi set <=> phase phi is an information bit
+};
+
+__device__ __forceinline__ float f_op(float a, float b) {
+    // polar.py:122-123 : sign(a) sign(b) min(|a|,|b|)   (exact in fp32)
+    float mn = fminf(fabsf(a), fabsf(b));
+    uint32_t s = (__float_as_uint(a) ^ __float_as_uint(b)) & 0x80000000u;
+    return __uint_as_float(__float_as_uint(mn) | s);
+}
+__device__ __forceinline__ float g_op(float a, float b, uint32_t bit) {
+    // polar.py:126-127 : b + (1-2c) a
+    return b + __uint_as_float(__float_as_uint(a) ^ (bit << 31));
+}
+
+// log(1+exp(-|L|)) -- shared part of both softplus branches (scl.py:102-105).
+__device__ __forceinline__ float softplus_tail(float L) { return log1pf(expf(-fabsf(L))); }
+
+__device__ __forceinline__ bool info_bit(const Code& c, int phi) { return (c.info_mask[phi >> 5] >> (phi & 31)) & 1u; }
+
+// ---------------------------------------------------------------------------
+// Per-warp shared-memory view.
+// ---------------------------------------------------------------------------
+template <int MP>
+struct WarpMem {
+    float* tree;          // [(2^n - 2)][32]   heights 1..n-1, lane-interleaved
+    float* chan;          // [FPW][N+1]        channel LLRs (height n), shared by the MP paths of a frame
+    unsigned long long* xchg;  // [32][2]      candidate keys for the rank exchange
+    static constexpr int FPW = 32 / MP;
+    __host__ __device__ static size_t bytes(int N) {
+        size_t t = (size_t)(N >= 4 ? N - 2 : 2) * 32 * 4;
+        size_t c = (size_t)FPW * (N + 1) * 4;
+        c = (c + 15) & ~(size_t)15;
+        return t + c + 32 * 16;
+    }
+    __device__ void carve(unsigned char* base, int N) {
+        size_t t = (size_t)(N >= 4 ? N - 2 : 2) * 32 * 4;
+        size_t c = ((size_t)FPW * (N + 1) * 4 + 15) & ~(size_t)15;
+        tree = reinterpret_cast<float*>(base);
+        chan = reinterpret_cast<float*>(base + t);
+        xchg = reinterpret_cast<unsigned long long*>(base + t + c);
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Bit-packed partial sums.  Height h holds 2^h bits:
+//   h = 0..4 -> word 0, bit offset 2^h - 1 ; h = 5 -> word 1 ; h = 6 -> words 2,3 ;
+//   h = 7 -> words 4..7 ; h = 8 -> words 8..15.
+// ---------------------------------------------------------------------------
+template <int LOGMAX> struct BitsCfg { static constexpr int BW = (LOGMAX <= 7) ? 4 : 16; static constexpr int XW = (1 << LOGMAX) / 32 > 0 ? (1 << LOGMAX) / 32 : 1; };
+
+template <int H, int BW>
+__device__ __forceinline__ uint32_t left_bit(const uint32_t (&bw)[BW], int i) {
+    // bit i of the left-child buffer at height H (H < 5: static field of word 0)
+    if constexpr (H < 5) return (bw[0] >> (((1 << H) - 1) + i)) & 1u;
+    else return 0;  // H >= 5 handled word-wise by the callers
+}
+
+// Upward propagation after deciding `bit` at a phase with T trailing ones
+// (scl.py:84-99).  cur (2^T bits) is returned in cw[]; the caller stores it as
+// the left buffer of height T, or takes it as x^ when T == n.
+template <int T, int BW, int CW>
+__device__ __forceinline__ void ascend(const uint32_t (&bw)[BW], uint32_t bit, uint32_t (&cw)[CW]) {
+    uint32_t cur = bit;
+#pragma unroll
+    for (int h = 0; h < (T < 5 ? T : 5); ++h) {
+        uint32_t L = (bw[0] >> ((1 << h) - 1)) & ((h == 5) ? 0xffffffffu : ((1u << (1 << h)) - 1u));
+        cur = (L ^ cur) | (cur << (1 << h));
+    }
+    cw[0] = cur;
+    if constexpr (T >= 6) {           // height 5 buffer = word 1
+        cw[0] = bw[1] ^ cur; cw[1] = cur;
+    }
+    if constexpr (T >= 7) {           // height 6 buffer = words 2,3
+        uint32_t c0 = cw[0], c1 = cw[1];
+        cw[0] = bw[2] ^ c0; cw[1] = bw[3] ^ c1; cw[2] = c0; cw[3] = c1;
+    }
+    if constexpr (T >= 8 && BW >= 8) {  // height 7 buffer = words 4..7
+        uint32_t c[4] = {cw[0], cw[1], cw[2], cw[3]};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { cw[k] = bw[4 + k] ^ c[k]; cw[4 + k] = c[k]; }
+    }
+    if constexpr (T >= 9 && BW >= 16) {  // height 8 buffer = words 8..15
+        uint32_t c[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) c[k] = cw[k];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { cw[k] = bw[8 + k] ^ c[k]; cw[8 + k] = c[k]; }
+    }
+}
+
+template <int T, int BW, int CW>
+__device__ __forceinline__ void store_height(uint32_t (&bw)[BW], const uint32_t (&cw)[CW]) {
+    if constexpr (T < 5) {
+        const uint32_t mask = ((1u << (1 << T)) - 1u) << ((1 << T) - 1);
+        bw[0] = (bw[0] & ~mask) | (cw[0] << ((1 << T) - 1));
+    } else if constexpr (T == 5) { bw[1] = cw[0]; }
+    else if constexpr (T == 6) { bw[2] = cw[0]; bw[3] = cw[1]; }
+    else if constexpr (T == 7 && BW >= 8) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) bw[4 + k] = cw[k];
+    } else if constexpr (T == 8 && BW >= 16) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bw[8 + k] = cw[k];
+    }
+}
+
+// GF(2) polar transform of an N-bit word held in XW registers (polar.py:17-29).
+template <int XW>
+__device__ __forceinline__ void transform_words(uint32_t (&x)[XW], int n) {
+    // stages inside a word
+    const uint32_t m[5] = {0x55555555u, 0x33333333u, 0x0f0f0f0fu, 0x00ff00ffu, 0x0000ffffu};
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        if (s < n) {
+#pragma unroll
+            for (int w = 0; w < XW; ++w) x[w] ^= (x[w] >> (1 << s)) & m[s];
+        }
+    }
+    // stages across words: stage s>=5 pairs word w with w + 2^(s-5)
+#pragma unroll
+    for (int s = 5; s < 5 + 4; ++s) {
+        const int d = 1 << (s - 5);
+        if (s < n && d < XW) {
+#pragma unroll
+            for (int w = 0; w < XW; ++w)
+                if ((w & d) == 0 && w + d < XW) x[w] ^= x[w + d];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Path state (registers of one lane).
+// ---------------------------------------------------------------------------
+template <int LOGMAX>
+struct Path {
+    static constexpr int BW = BitsCfg<LOGMAX>::BW;
+    static constexpr int XW = BitsCfg<LOGMAX>::XW;
+    uint32_t P;            // 4-bit slot pointer per height h (field h-1), heights 1..n-1
+    uint32_t bw[BW];       // partial-sum left buffers
+    uint32_t xh[XW];       // x^ after the last phase
+    double m;              // path metric (scl.py:19), fp64 accumulation
+    uint32_t r;            // rank in the reference's sorted list
+    bool alive;
+};
+
+// ---------------------------------------------------------------------------
+// LLR tree evaluation.
+// ---------------------------------------------------------------------------
+template <int MP, int LOGMAX>
+struct Tree {
+    using PathT = Path<LOGMAX>;
+    static constexpr int BW = PathT::BW;
+
+    // down from 2^H register values to the leaf; heights H-1..1 are stored in the own slot
+    template <int H>
+    static __device__ __forceinline__ float reg_chain(float (&v)[1 << H], float* own) {
+        if constexpr (H == 0) return v[0];
+        else {
+            float w[(1 << H) / 2 > 0 ? (1 << H) / 2 : 1];
+#pragma unroll
+            for (int i = 0; i < (1 << (H - 1)); ++i) {
+                w[i] = f_op(v[i], v[i + (1 << (H - 1))]);
+                if constexpr (H - 1 >= 1) own[(((1 << (H - 1)) - 2) + i) * 32] = w[i];
+            }
+            return reg_chain<H - 1>(w, own);
+        }
+    }
+
+    // Produce height H from height H+1 stored at src[i*stride] (OP 0 = f, 1 = g with the left bits
+    // of height H), store it in the own slot, continue with f down to the leaf.  Returns the leaf LLR.
+    template <int H, int OP>
+    static __device__ __forceinline__ float produce(const float* src, int stride, const uint32_t (&bw)[BW], float* own) {
+        constexpr int S = 1 << H;
+        if constexpr (H <= 3) {
+            float v[S];
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+                float a = src[i * stride], b = src[(i + S) * stride];
+                v[i] = OP ? g_op(a, b, left_bit<H, BW>(bw, i)) : f_op(a, b);
+                if constexpr (H >= 1) own[((S - 2) + i) * 32] = v[i];
+            }
+            return reg_chain<H>(v, own);
+        } else {
+            float* dst = own + (S - 2) * 32;
+            if constexpr (OP == 0) {
+#pragma unroll 4
+                for (int i = 0; i < S; ++i) dst[i * 32] = f_op(src[i * stride], src[(i + S) * stride]);
+            } else if constexpr (H == 4) {
+                const uint32_t bits = bw[0] >> 15;
+#pragma unroll 4
+                for (int i = 0; i < S; ++i) dst[i * 32] = g_op(src[i * stride], src[(i + S) * stride], (bits >> i) & 1u);
+            } else {
+                constexpr int W0 = (H == 5) ? 1 : (H == 6) ? 2 : (H == 7) ? 4 : 8;  // first word of height H
+#pragma unroll
+                for (int w = 0; w < S / 32; ++w) {
+                    const uint32_t bits = bw[(W0 + w) < BW ? (W0 + w) : 0];
+#pragma unroll 4
+                    for (int j = 0; j < 32; ++j) {
+                        const int i = w * 32 + j;
+                        dst[i * 32] = g_op(src[i * stride], src[(i + S) * stride], (bits >> j) & 1u);
+                    }
+                }
+            }
+            return produce<H - 1, 0>(dst, 32, bw, own);
+        }
+    }
+};
+
+}  // namespace pb
