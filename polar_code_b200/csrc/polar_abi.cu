@@ -1,0 +1,490 @@
+// polar_abi.cu -- C-ABI of libpolar_b200.so (see include/polar_b200.h) and kernel dispatch.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/polar_b200.h"
+#include "polar_kernels.cuh"
+#include "polar_sweep.cuh"
+
+using namespace pb;
+
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(x)                                                                                   \
+    do {                                                                                              \
+        cudaError_t _e = (x);                                                                         \
+        if (_e != cudaSuccess) return fail(PB200_ECUDA, "%s failed: %s", #x, cudaGetErrorString(_e)); \
+    } while (0)
+
+extern "C" const char* pb200_last_error(void) { return g_err.c_str(); }
+extern "C" int pb200_version(void) { return 100; }
+extern "C" int pb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Code construction (host, float64): polar/polar.py:37-103
+// ---------------------------------------------------------------------------------------------------
+static int ilog2_exact(int N) {
+    if (N <= 0 || (N & (N - 1))) return -1;
+    int n = 0;
+    while ((1 << n) < N) ++n;
+    return n;
+}
+
+static double phi_inverse(double x) {  // polar.py:51-58
+    if (x > 12.0) return 0.9861 * x - 2.3152;
+    if (x > 3.5) return x * (0.009005 * x + 0.7694) - 0.9507;
+    if (x > 1.0) return x * (0.062883 * x + 0.3678) - 0.1627;
+    return x * (0.2202 * x + 0.06448);
+}
+
+extern "C" int pb200_construct_info_set(int N, int K, int method, double design_snr_db, int32_t* out) {
+    const int n = ilog2_exact(N);
+    if (n < 0) return fail(PB200_EINVAL, "N must be a power of two");
+    if (!(0 < K && K <= N)) return fail(PB200_EINVAL, "K must satisfy 0 < K <= N");
+    std::vector<double> metric(N, 0.0);
+    if (method == 1) {  // polarization weights, polar.py:37-48
+        for (int idx = 0; idx < N; ++idx) {
+            double w = 0.0;
+            for (int j = 0; j < n; ++j)
+                if ((idx >> j) & 1) w += pow(2.0, j / 4.0);
+            metric[idx] = w;
+        }
+    } else if (method == 0) {  // Gaussian approximation, polar.py:61-82
+        const double sigma_sq = 1.0 / (2.0 * ((double)K / (double)N) * pow(10.0, design_snr_db / 10.0));
+        metric[0] = 2.0 / sigma_sq;
+        for (int level = 1; level <= n; ++level) {
+            const int half = (1 << level) >> 1;
+            for (int j = 0; j < half; ++j) {
+                const double T = metric[j];
+                metric[j] = phi_inverse(T);
+                metric[half + j] = 2.0 * T;
+            }
+        }
+        for (int i = 0; i < N; ++i) metric[i] = 0.5 - 0.5 * erf(sqrt(std::max(metric[i], 1e-12)) / 2.0);
+    } else {
+        return fail(PB200_EINVAL, "Unsupported construction method");
+    }
+    std::vector<int> order(N);
+    for (int i = 0; i < N; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return metric[a] < metric[b]; });
+    std::vector<int> best(order.begin(), order.begin() + K);
+    std::sort(best.begin(), best.end());
+    for (int i = 0; i < K; ++i) out[i] = best[i];
+    return PB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Engine
+// ---------------------------------------------------------------------------------------------------
+struct KernelCfg { int wpc, ctas_per_sm, smem, regs; };
+
+struct pb200_engine {
+    int device = 0, sms = 0;
+    Code code{};
+    std::vector<int> info_pos;
+    unsigned long long poly = 0;   // CRC polynomial incl. leading 1 (0 = none)
+    int K = 0;
+    Tables tb{};
+    int16_t* d_info_pos = nullptr;
+    uint32_t* d_crc_tab = nullptr;
+    int16_t* d_rm_src = nullptr;
+    int16_t* d_tx_src = nullptr;   // NR transmit gather: tx[e] = code[tx_src[e]] or pad (-1)
+    uint32_t* d_enc_tab = nullptr; // sweep encoder tables
+    std::map<std::tuple<int, int, int>, KernelCfg> cfg_cache;
+    // host-buffer pipeline
+    cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
+    float* d_stage_llr[3] = {nullptr, nullptr, nullptr};
+    uint8_t* d_stage_bits[3] = {nullptr, nullptr, nullptr};
+    uint8_t* d_stage_ok[3] = {nullptr, nullptr, nullptr};
+    uint32_t* d_stage_flags[3] = {nullptr, nullptr, nullptr};
+    int64_t stage_frames = 0;
+    int stage_len = 0;
+    // NR + DL-SCL state
+    int16_t* d_rm_dst = nullptr;   // [N] de-rate-matched position -> internal index
+    unsigned char* d_q[2] = {nullptr, nullptr};
+    size_t q_bytes = 0;
+    unsigned int* d_q_counts = nullptr;
+    int q_counts_n = 0;
+};
+int sweep_build_tables(pb200_engine* e);
+
+static int parse_poly(const char* s, unsigned long long* poly, int* deg) {
+    if (!s || !*s) return fail(PB200_EINVAL, "CRC polynomial string must be non-empty");
+    char* end = nullptr;
+    const unsigned long long v = strtoull(s, &end, 16);
+    if (end == s || *end != 0) return fail(PB200_EINVAL, "CRC polynomial must be a hex string");
+    int len = 0;
+    while (len < 64 && (v >> len)) ++len;
+    if (len - 1 <= 0) return fail(PB200_EINVAL, "Polynomial degree must be positive");
+    *poly = v;
+    *deg = len - 1;
+    return PB200_OK;
+}
+
+// x^e mod g(x) as a deg-bit integer
+static unsigned long long xpow_mod(int e, unsigned long long poly, int deg) {
+    const unsigned long long low = poly & ((1ull << deg) - 1ull);
+    unsigned long long r = 1;  // x^0
+    if (deg == 0) return 0;
+    for (int i = 0; i < e; ++i) {
+        const unsigned long long top = (r >> (deg - 1)) & 1ull;
+        r = (r << 1) & ((1ull << deg) - 1ull);
+        if (top) r ^= low;
+    }
+    return r;
+}
+
+static void host_transform(std::vector<uint8_t>& x) {  // polar.py:17-29
+    const int N = (int)x.size();
+    for (int step = 1; step < N; step <<= 1)
+        for (int start = 0; start < N; start += 2 * step)
+            for (int i = 0; i < step; ++i) x[start + i] ^= x[start + step + i];
+}
+
+extern "C" int pb200_create(pb200_engine** out, int device, int N, const int32_t* info_set, int K, const char* crc_poly) {
+    if (!out) return fail(PB200_EINVAL, "out is NULL");
+    *out = nullptr;
+    const int n = ilog2_exact(N);
+    if (n < 0) return fail(PB200_EINVAL, "N must be a power of two");
+    if (N < 2) return fail(PB200_ENOSUP, "N must be at least 2");
+    if (N > PB200_MAX_N) return fail(PB200_ENOSUP, "N > %d is not supported by this build", PB200_MAX_N);
+    if (K <= 0 || K > N || !info_set) return fail(PB200_EINVAL, "info_set must hold 0 < K <= N indices");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(PB200_ECUDA, "no CUDA device: the polar_b200 engine has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(PB200_EINVAL, "device %d out of range", device);
+    CUDA_TRY(cudaSetDevice(device));
+    pb200_engine* e = new pb200_engine();
+    e->device = device;
+    cudaDeviceGetAttribute(&e->sms, cudaDevAttrMultiProcessorCount, device);
+    e->K = K;
+    e->code.N = N; e->code.n = n; e->code.K = K; e->code.M = 1; e->code.crc_deg = 0;
+    memset(e->code.info_mask, 0, sizeof e->code.info_mask);
+    e->info_pos.assign(info_set, info_set + K);
+    for (int j = 0; j < K; ++j) {
+        const int p = info_set[j];
+        if (p < 0 || p >= N) { delete e; return fail(PB200_EINVAL, "info_set indices out of range"); }
+        if (j > 0 && info_set[j] <= info_set[j - 1]) { delete e; return fail(PB200_EINVAL, "info_set must be strictly increasing"); }
+        e->code.info_mask[p >> 5] |= 1u << (p & 31);
+    }
+    int deg = 0;
+    if (crc_poly) {
+        int rc = parse_poly(crc_poly, &e->poly, &deg);
+        if (rc) { delete e; return rc; }
+        if (deg > 32) { delete e; return fail(PB200_ENOSUP, "CRC degree > 32 is not supported by the fused check"); }
+        if (K <= deg) { delete e; return fail(PB200_EINVAL, "Message too short for the provided CRC polynomial"); }
+    }
+    e->code.crc_deg = deg;
+    // tables
+    std::vector<int16_t> pos16(K);
+    for (int j = 0; j < K; ++j) pos16[j] = (int16_t)info_set[j];
+    const int nn = N >= 4 ? N / 4 : 1;
+    std::vector<uint32_t> crc_tab((size_t)nn * 16, 0);
+    if (deg) {
+        std::vector<uint32_t> S(N, 0);  // syndrome contribution of phase p
+        for (int j = 0; j < K; ++j) S[info_set[j]] = (uint32_t)xpow_mod(K - 1 - j, e->poly, deg);
+        for (int nib = 0; nib < nn; ++nib)
+            for (int v = 0; v < 16; ++v) {
+                uint32_t s = 0;
+                for (int b = 0; b < 4; ++b)
+                    if (((v >> b) & 1) && nib * 4 + b < N) s ^= S[nib * 4 + b];
+                crc_tab[nib * 16 + v] = s;
+            }
+    }
+    std::vector<int16_t> rm(N);
+    for (int i = 0; i < N; ++i) rm[i] = (int16_t)i;
+    auto up = [&](void** d, const void* h, size_t bytes) -> cudaError_t {
+        cudaError_t r = cudaMalloc(d, bytes);
+        if (r != cudaSuccess) return r;
+        return cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
+    };
+    cudaError_t ce;
+    if ((ce = up((void**)&e->d_info_pos, pos16.data(), pos16.size() * 2)) != cudaSuccess ||
+        (ce = up((void**)&e->d_crc_tab, crc_tab.data(), crc_tab.size() * 4)) != cudaSuccess ||
+        (ce = up((void**)&e->d_rm_src, rm.data(), rm.size() * 2)) != cudaSuccess) {
+        pb200_destroy(e);
+        return fail(PB200_ECUDA, "table upload failed: %s", cudaGetErrorString(ce));
+    }
+    e->tb.info_pos = e->d_info_pos;
+    e->tb.crc_tab = e->d_crc_tab;
+    e->tb.rm_src = e->d_rm_src;
+    e->tb.E = 0;
+    int rc = sweep_build_tables(e);
+    if (rc) { pb200_destroy(e); return rc; }
+    *out = e;
+    return PB200_OK;
+}
+
+extern "C" void pb200_destroy(pb200_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaFree(e->d_info_pos); cudaFree(e->d_crc_tab); cudaFree(e->d_rm_src); cudaFree(e->d_tx_src); cudaFree(e->d_enc_tab);
+    cudaFree(e->d_rm_dst); cudaFree(e->d_q[0]); cudaFree(e->d_q[1]); cudaFree(e->d_q_counts);
+    for (int i = 0; i < 3; ++i) {
+        if (e->hs[i]) cudaStreamDestroy(e->hs[i]);
+        cudaFree(e->d_stage_llr[i]); cudaFree(e->d_stage_bits[i]); cudaFree(e->d_stage_ok[i]); cudaFree(e->d_stage_flags[i]);
+    }
+    delete e;
+}
+
+// nr/polar/interleaver.py:10-37 + rate_match.py:8-39 folded into two gather tables.
+extern "C" int pb200_set_rate_matching(pb200_engine* e, int E) {
+    if (!e) return fail(PB200_EINVAL, "engine is NULL");
+    if (E < 0) return fail(PB200_EINVAL, "E must be >= 0");
+    CUDA_TRY(cudaSetDevice(e->device));
+    const int N = e->code.N;
+    cudaFree(e->d_tx_src);
+    e->d_tx_src = nullptr;
+    std::vector<int16_t> rm(N), rd(N);
+    if (E == 0) {
+        for (int i = 0; i < N; ++i) { rm[i] = (int16_t)i; rd[i] = (int16_t)i; }
+    } else {
+        const int block = 32, nb = (N + block - 1) / block, total = nb * block;
+        std::vector<int> order(total), inv(total);
+        for (int i = 0; i < total; ++i) order[i] = (i % block) * nb + (i / block);   // interleaver.py:20
+        for (int i = 0; i < total; ++i) inv[order[i]] = i;                           // argsort(order), :31-36
+        // receive side: internal[i] = derated[inv[i]] if inv[i] < N else 0.0 (zero padding, :33-34)
+        for (int i = 0; i < N; ++i) rm[i] = (int16_t)(inv[i] < N ? inv[i] : -1);
+        for (int p = 0; p < N; ++p) rd[p] = (int16_t)(order[p] < N ? order[p] : -1);
+        // transmit side: interleaved[k] = code[order[k]] or pad -1 (:17-21); rate_match: first E of the tiling (:8-16)
+        std::vector<int16_t> tx(E);
+        for (int t = 0; t < E; ++t) {
+            const int k = (E <= total) ? t : (t % total);
+            tx[t] = (int16_t)(order[k] < N ? order[k] : -1);
+        }
+        CUDA_TRY(cudaMalloc((void**)&e->d_tx_src, (size_t)E * 2));
+        CUDA_TRY(cudaMemcpy(e->d_tx_src, tx.data(), (size_t)E * 2, cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(cudaMemcpy(e->d_rm_src, rm.data(), (size_t)N * 2, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(e->d_rm_dst, rd.data(), (size_t)N * 2, cudaMemcpyHostToDevice));
+    e->tb.E = E;
+    return PB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Kernel selection
+// ---------------------------------------------------------------------------------------------------
+typedef void (*decode_fn)(const Code, const Tables, const DecodeArgs);
+
+template <int LOGMAX>
+static decode_fn pick_decode(int MP, bool forced, bool metric) {
+    if (!metric) return forced ? decode_kernel<1, LOGMAX, true, false> : decode_kernel<1, LOGMAX, false, false>;
+    switch (MP) {
+        case 1: return forced ? decode_kernel<1, LOGMAX, true, true> : decode_kernel<1, LOGMAX, false, true>;
+        case 2: return forced ? decode_kernel<2, LOGMAX, true, true> : decode_kernel<2, LOGMAX, false, true>;
+        case 4: return forced ? decode_kernel<4, LOGMAX, true, true> : decode_kernel<4, LOGMAX, false, true>;
+        default: return forced ? decode_kernel<8, LOGMAX, true, true> : decode_kernel<8, LOGMAX, false, true>;
+    }
+}
+
+static int round_mp(int M) { return M <= 1 ? 1 : M <= 2 ? 2 : M <= 4 ? 4 : 8; }
+
+static size_t warp_bytes(int MP, int N, int xk) {
+    switch (MP) {
+        case 1: return WarpMem<1>::bytes(N, xk);
+        case 2: return WarpMem<2>::bytes(N, xk);
+        case 4: return WarpMem<4>::bytes(N, xk);
+        default: return WarpMem<8>::bytes(N, xk);
+    }
+}
+
+// Choose warps per CTA so that resident warps per SM are maximal for this kernel's registers and smem.
+static int choose_cfg(pb200_engine* e, const void* fn, int MP, int key_kind, size_t wb, KernelCfg* out) {
+    auto key = std::make_tuple(MP, key_kind, (int)e->tb.E);
+    auto it = e->cfg_cache.find(key);
+    if (it != e->cfg_cache.end()) { *out = it->second; return PB200_OK; }
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, fn));
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes));
+    KernelCfg best{0, 0, 0, fa.numRegs};
+    int best_warps = 0;
+    for (int wpc = 32; wpc >= 1; --wpc) {
+        const size_t smem = wb * wpc;
+        if (smem > (size_t)(227 * 1024) - fa.sharedSizeBytes) continue;
+        if (wpc * 32 > fa.maxThreadsPerBlock) continue;
+        int blocks = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, fn, wpc * 32, smem) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (blocks * wpc > best_warps) { best_warps = blocks * wpc; best = KernelCfg{wpc, blocks, (int)smem, fa.numRegs}; }
+    }
+    if (best_warps == 0) return fail(PB200_ECUDA, "no launch configuration fits (N=%d, MP=%d)", e->code.N, MP);
+    e->cfg_cache[key] = best;
+    *out = best;
+    return PB200_OK;
+}
+
+static int launch_decode(pb200_engine* e, int M, bool metric, const DecodeArgs& a, cudaStream_t st) {
+    const int MP = metric ? round_mp(M) : 1;
+    const bool forced = a.force != nullptr;
+    decode_fn fn = e->code.n <= 7 ? pick_decode<7>(MP, forced, metric) : pick_decode<9>(MP, forced, metric);
+    KernelCfg kc;
+    int rc = choose_cfg(e, (const void*)fn, MP, (forced ? 1 : 0) | (metric ? 2 : 0), warp_bytes(MP, e->code.N, 0), &kc);
+    if (rc) return rc;
+    Code code = e->code;
+    code.M = metric ? M : 1;
+    const int fpw = 32 / MP;
+    const int64_t groups = (a.B + fpw - 1) / fpw;
+    const int64_t want = (groups + kc.wpc - 1) / kc.wpc;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)e->sms * kc.ctas_per_sm));
+    fn<<<grid, kc.wpc * 32, kc.smem, st>>>(code, e->tb, a);
+    CUDA_TRY(cudaGetLastError());
+    return PB200_OK;
+}
+
+static int check_decode_args(pb200_engine* e, const float* llr, int64_t B, int in_len, int M) {
+    if (!e) return fail(PB200_EINVAL, "engine is NULL");
+    if (M <= 0) return fail(PB200_EINVAL, "List size M must be positive");
+    if (M > PB200_MAX_M) return fail(PB200_ENOSUP, "list size M > %d is not supported by this build", PB200_MAX_M);
+    if (B < 0) return fail(PB200_EINVAL, "B must be >= 0");
+    if (B > 0 && !llr) return fail(PB200_EINVAL, "llr is NULL");
+    const int want = e->tb.E ? e->tb.E : e->code.N;
+    if (in_len != want) return fail(PB200_EINVAL, "llr rows must have length %d (got %d)", want, in_len);
+    return PB200_OK;
+}
+
+extern "C" int pb200_kernel_info(pb200_engine* e, int M, int* wpc, int* ctas, int* smem, int* regs) {
+    if (!e) return fail(PB200_EINVAL, "engine is NULL");
+    if (M <= 0 || M > PB200_MAX_M) return fail(PB200_EINVAL, "bad M");
+    CUDA_TRY(cudaSetDevice(e->device));
+    const int MP = round_mp(M);
+    decode_fn fn = e->code.n <= 7 ? pick_decode<7>(MP, false, true) : pick_decode<9>(MP, false, true);
+    KernelCfg kc;
+    int rc = choose_cfg(e, (const void*)fn, MP, 2, warp_bytes(MP, e->code.N, 0), &kc);
+    if (rc) return rc;
+    if (wpc) *wpc = kc.wpc;
+    if (ctas) *ctas = kc.ctas_per_sm;
+    if (smem) *smem = kc.smem;
+    if (regs) *regs = kc.regs;
+    return PB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Encoder / CRC
+// ---------------------------------------------------------------------------------------------------
+extern "C" int pb200_encode_batch(pb200_engine* e, const uint8_t* msg, uint8_t* code, int64_t B, void* stream) {
+    if (!e) return fail(PB200_EINVAL, "engine is NULL");
+    if (B < 0 || (B > 0 && (!msg || !code))) return fail(PB200_EINVAL, "bad buffers");
+    if (B == 0) return PB200_OK;
+    CUDA_TRY(cudaSetDevice(e->device));
+    encode_kernel<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(e->code, e->tb, msg, code, B);
+    CUDA_TRY(cudaGetLastError());
+    return PB200_OK;
+}
+
+static int crc_common(const char* poly, const uint8_t* msg, int64_t B, int L, uint8_t* attach, uint8_t* ok, void* stream) {
+    unsigned long long p;
+    int deg;
+    int rc = parse_poly(poly, &p, &deg);
+    if (rc) return rc;
+    if (deg > 63) return fail(PB200_ENOSUP, "CRC degree > 63 is not supported");
+    if (L < 0 || B < 0) return fail(PB200_EINVAL, "bad sizes");
+    if (ok && L <= deg) return fail(PB200_EINVAL, "Message too short for the provided CRC polynomial");
+    if (B == 0) return PB200_OK;
+    if (!msg) return fail(PB200_EINVAL, "msg is NULL");
+    crc_kernel<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p, deg, msg, L, B, attach, ok);
+    CUDA_TRY(cudaGetLastError());
+    return PB200_OK;
+}
+extern "C" int pb200_crc_attach_batch(const char* poly, const uint8_t* msg, uint8_t* out, int64_t B, int L, void* stream) {
+    if (!out && B > 0) return fail(PB200_EINVAL, "out is NULL");
+    return crc_common(poly, msg, B, L, out, nullptr, stream);
+}
+extern "C" int pb200_crc_check_batch(const char* poly, const uint8_t* msg, uint8_t* ok, int64_t B, int L, void* stream) {
+    if (!ok && B > 0) return fail(PB200_EINVAL, "ok is NULL");
+    return crc_common(poly, msg, B, L, nullptr, ok, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Decoders
+// ---------------------------------------------------------------------------------------------------
+extern "C" int pb200_sc_decode_batch(pb200_engine* e, const float* llr, int64_t B, int in_len, uint8_t* bits, void* stream) {
+    int rc = check_decode_args(e, llr, B, in_len, 1);
+    if (rc) return rc;
+    if (B == 0) return PB200_OK;
+    if (!bits) return fail(PB200_EINVAL, "bits is NULL");
+    CUDA_TRY(cudaSetDevice(e->device));
+    DecodeArgs a{};
+    a.llr = llr; a.B = B; a.in_len = in_len; a.best_bits = bits;
+    return launch_decode(e, 1, false, a, (cudaStream_t)stream);
+}
+
+extern "C" int pb200_scl_decode_batch(pb200_engine* e, const float* llr, int64_t B, int in_len, const int8_t* force, int M,
+                                      const pb200_scl_out* out, void* stream) {
+    int rc = check_decode_args(e, llr, B, in_len, M);
+    if (rc) return rc;
+    if (!out) return fail(PB200_EINVAL, "out is NULL");
+    if (B == 0) return PB200_OK;
+    CUDA_TRY(cudaSetDevice(e->device));
+    DecodeArgs a{};
+    a.llr = llr; a.B = B; a.in_len = in_len; a.force = force;
+    a.cand = out->cand; a.metrics = out->metrics; a.info_llrs = out->info_llrs; a.n_cand = out->n_cand;
+    a.best_idx = out->best_idx; a.best_bits = out->best_bits; a.best_words = out->best_words; a.crc_ok = out->crc_ok;
+    a.flags = out->flags;
+    return launch_decode(e, M, true, a, (cudaStream_t)stream);
+}
+
+// Host buffers in, host buffers out: chunked, triple-buffered copy/compute overlap on internal streams.
+extern "C" int pb200_scl_decode_host(pb200_engine* e, const float* h_llr, int64_t B, int in_len, int M, uint8_t* h_bits,
+                                     uint8_t* h_ok, uint32_t* h_flags) {
+    int rc = check_decode_args(e, h_llr, B, in_len, M);
+    if (rc) return rc;
+    if (B == 0) return PB200_OK;
+    CUDA_TRY(cudaSetDevice(e->device));
+    const int K = e->code.K;
+    const int64_t chunk = std::min<int64_t>(B, 1 << 18);
+    if (e->stage_frames < chunk || e->stage_len != in_len) {
+        for (int i = 0; i < 3; ++i) {
+            cudaFree(e->d_stage_llr[i]); cudaFree(e->d_stage_bits[i]); cudaFree(e->d_stage_ok[i]); cudaFree(e->d_stage_flags[i]);
+            e->d_stage_llr[i] = nullptr; e->d_stage_bits[i] = nullptr; e->d_stage_ok[i] = nullptr; e->d_stage_flags[i] = nullptr;
+            if (!e->hs[i]) CUDA_TRY(cudaStreamCreateWithFlags(&e->hs[i], cudaStreamNonBlocking));
+            CUDA_TRY(cudaMalloc((void**)&e->d_stage_llr[i], (size_t)chunk * in_len * 4));
+            CUDA_TRY(cudaMalloc((void**)&e->d_stage_bits[i], (size_t)chunk * K));
+            CUDA_TRY(cudaMalloc((void**)&e->d_stage_ok[i], (size_t)chunk));
+            CUDA_TRY(cudaMalloc((void**)&e->d_stage_flags[i], (size_t)chunk * 4));
+        }
+        e->stage_frames = chunk;
+        e->stage_len = in_len;
+    }
+    int64_t done = 0;
+    int slot = 0;
+    while (done < B) {
+        const int64_t nb = std::min<int64_t>(chunk, B - done);
+        cudaStream_t st = e->hs[slot];
+        CUDA_TRY(cudaMemcpyAsync(e->d_stage_llr[slot], h_llr + done * in_len, (size_t)nb * in_len * 4, cudaMemcpyHostToDevice, st));
+        DecodeArgs a{};
+        a.llr = e->d_stage_llr[slot]; a.B = nb; a.in_len = in_len;
+        a.best_bits = e->d_stage_bits[slot]; a.crc_ok = e->d_stage_ok[slot]; a.flags = e->d_stage_flags[slot];
+        rc = launch_decode(e, M, true, a, st);
+        if (rc) return rc;
+        if (h_bits) CUDA_TRY(cudaMemcpyAsync(h_bits + done * K, e->d_stage_bits[slot], (size_t)nb * K, cudaMemcpyDeviceToHost, st));
+        if (h_ok) CUDA_TRY(cudaMemcpyAsync(h_ok + done, e->d_stage_ok[slot], (size_t)nb, cudaMemcpyDeviceToHost, st));
+        if (h_flags) CUDA_TRY(cudaMemcpyAsync(h_flags + done, e->d_stage_flags[slot], (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+        done += nb;
+        slot = (slot + 1) % 3;
+    }
+    for (int i = 0; i < 3; ++i) CUDA_TRY(cudaStreamSynchronize(e->hs[i]));
+    return PB200_OK;
+}
+
+#include "polar_abi_sweep.inl"

@@ -1,0 +1,249 @@
+// polar_abi_sweep.inl -- host side of the Monte-Carlo sweep, DL-SCL rounds, channel generator, NR encoder.
+// Included at the end of polar_abi.cu.
+
+typedef void (*sweep_fn)(const Code, const Tables, const SweepArgs);
+
+template <int LOGMAX>
+static sweep_fn pick_sweep(int MP, bool round) {
+    switch (MP) {
+        case 1: return round ? dl_round_kernel<1, LOGMAX> : sweep_kernel<1, LOGMAX>;
+        case 2: return round ? dl_round_kernel<2, LOGMAX> : sweep_kernel<2, LOGMAX>;
+        case 4: return round ? dl_round_kernel<4, LOGMAX> : sweep_kernel<4, LOGMAX>;
+        default: return round ? dl_round_kernel<8, LOGMAX> : sweep_kernel<8, LOGMAX>;
+    }
+}
+
+int sweep_build_tables(pb200_engine* e) {
+    const int N = e->code.N;
+    std::vector<int16_t> id(N);
+    for (int i = 0; i < N; ++i) id[i] = (int16_t)i;
+    if (cudaMalloc((void**)&e->d_rm_dst, (size_t)N * 2) != cudaSuccess) return fail(PB200_ECUDA, "cudaMalloc rm_dst failed");
+    if (cudaMemcpy(e->d_rm_dst, id.data(), (size_t)N * 2, cudaMemcpyHostToDevice) != cudaSuccess) return fail(PB200_ECUDA, "upload rm_dst failed");
+    return PB200_OK;
+}
+
+static size_t entry_bytes(const pb200_engine* e) { return e->code.n <= 7 ? sizeof(DlEntry<4>) : sizeof(DlEntry<16>); }
+
+static int ensure_queues(pb200_engine* e, long long frames, int retries) {
+    const size_t need = (size_t)frames * entry_bytes(e);
+    if (e->q_bytes < need) {
+        cudaFree(e->d_q[0]); cudaFree(e->d_q[1]);
+        e->d_q[0] = e->d_q[1] = nullptr; e->q_bytes = 0;
+        CUDA_TRY(cudaMalloc((void**)&e->d_q[0], need));
+        CUDA_TRY(cudaMalloc((void**)&e->d_q[1], need));
+        e->q_bytes = need;
+    }
+    if (e->q_counts_n < retries + 2) {
+        cudaFree(e->d_q_counts);
+        e->d_q_counts = nullptr; e->q_counts_n = 0;
+        CUDA_TRY(cudaMalloc((void**)&e->d_q_counts, sizeof(unsigned int) * (retries + 2)));
+        e->q_counts_n = retries + 2;
+    }
+    return PB200_OK;
+}
+
+static void fill_chan(pb200_engine* e, const pb200_sweep_cfg* c, ChanCfg* cc) {
+    cc->k0 = (uint32_t)(c->seed & 0xffffffffu);
+    cc->k1 = (uint32_t)(c->seed >> 32) + 0x9E3779B9u * c->stream_id;
+    cc->sigma = (float)sqrt(c->noise_var);
+    cc->scale = (float)(2.0 / c->noise_var);
+    const double nvu = c->noise_var_uncoded > 0 ? c->noise_var_uncoded : 1.0;
+    cc->sigma_u = (float)sqrt(nvu);
+    cc->scale_u = (float)(2.0 / nvu);
+    cc->kp = c->k_payload;
+    cc->include_uncoded = c->include_uncoded;
+    cc->poly = e->poly;
+    cc->deg = e->code.crc_deg;
+    cc->tx_src = e->d_tx_src;
+    cc->rm_dst = e->d_rm_dst;
+}
+
+static int check_sweep_cfg(pb200_engine* e, const pb200_sweep_cfg* c) {
+    if (!e || !c) return fail(PB200_EINVAL, "engine/cfg is NULL");
+    if (c->M <= 0) return fail(PB200_EINVAL, "List size M must be positive");
+    if (c->M > PB200_MAX_M) return fail(PB200_ENOSUP, "list size M > %d is not supported by this build", PB200_MAX_M);
+    if (!(c->noise_var > 0)) return fail(PB200_EINVAL, "noise_var must be positive");
+    if (c->k_payload <= 0 || c->k_payload > e->code.K) return fail(PB200_EINVAL, "k_payload must be in 1..K");
+    if (c->k_payload < e->code.K) {
+        if (e->code.crc_deg == 0) return fail(PB200_EINVAL, "k_payload < K needs a CRC polynomial");
+        if (e->code.K - c->k_payload != e->code.crc_deg) return fail(PB200_EINVAL, "K - k_payload must equal the CRC degree");
+    }
+    const int E = c->E == e->code.N ? (e->tb.E ? c->E : 0) : c->E;
+    if (E != e->tb.E && !(E == 0 && e->tb.E == 0)) return fail(PB200_EINVAL, "cfg.E does not match pb200_set_rate_matching");
+    if (c->n_frames < 0 || c->frame_begin < 0) return fail(PB200_EINVAL, "bad frame range");
+    if (c->bit_error_span < 0 || c->bit_error_span > e->code.K) return fail(PB200_EINVAL, "bit_error_span must be in 0..K");
+    return PB200_OK;
+}
+
+// Shared driver: baseline launch + `retries` round launches over [frame_begin, frame_begin + n_frames).
+static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
+    const int MP = round_mp(M);
+    const bool big = e->code.n > 7;
+    Code code = e->code;
+    code.M = M;
+    sweep_fn base = big ? pick_sweep<9>(MP, false) : pick_sweep<7>(MP, false);
+    sweep_fn round = big ? pick_sweep<9>(MP, true) : pick_sweep<7>(MP, true);
+    KernelCfg kb, kr;
+    int rc = choose_cfg(e, (const void*)base, MP, 4, warp_bytes(MP, code.N, 0), &kb);
+    if (rc) return rc;
+    const int fpw = 32 / MP;
+    const long long piece_max = 1ll << 22;
+    const long long total = a.n_frames, begin0 = a.frame_begin;
+    const long long out_base = a.frame_begin;   // per-frame outputs are indexed by frame - frame_begin of the whole call
+    (void)out_base;
+    for (long long off = 0; off < total; off += piece_max) {
+        const long long nf = std::min(piece_max, total - off);
+        SweepArgs p = a;
+        // per-frame outputs / llr rows stay indexed relative to the whole call: shift the base pointers
+        p.frame_begin = begin0 + off;
+        p.n_frames = nf;
+        if (p.llr) p.llr += (size_t)off * p.in_len;
+        if (p.frame_bit_errors) p.frame_bit_errors += off;
+        if (p.frame_work) p.frame_work += off;
+        if (p.best_bits) p.best_bits += (size_t)off * code.K;
+        if (p.best_words) p.best_words += (size_t)off * (code.N >= 32 ? code.N / 32 : 1);
+        if (p.success) p.success += off;
+        if (p.n_attempts) p.n_attempts += off;
+        if (p.tried) p.tried += (size_t)off * p.R;
+        if (p.flags) p.flags += off;
+        if (a.retries > 0) {
+            rc = ensure_queues(e, nf, a.retries);
+            if (rc) return rc;
+            CUDA_TRY(cudaMemsetAsync(e->d_q_counts, 0, sizeof(unsigned int) * (a.retries + 2), st));
+            p.q_capacity = (unsigned int)nf;
+            p.q_out = e->d_q[0];
+            p.q_out_count = e->d_q_counts;
+        } else {
+            // retries <= 0: nothing is ever enqueued, but the kernel still takes a valid counter
+            rc = ensure_queues(e, 1, 0);
+            if (rc) return rc;
+            CUDA_TRY(cudaMemsetAsync(e->d_q_counts, 0, sizeof(unsigned int) * 2, st));
+            p.q_capacity = 1;
+            p.q_out = e->d_q[0];
+            p.q_out_count = e->d_q_counts;
+        }
+        const long long groups = (nf + fpw - 1) / fpw;
+        const long long want = (groups + kb.wpc - 1) / kb.wpc;
+        const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)e->sms * kb.ctas_per_sm));
+        base<<<grid, kb.wpc * 32, kb.smem, st>>>(code, e->tb, p);
+        CUDA_TRY(cudaGetLastError());
+        if (a.retries > 0) {
+            rc = choose_cfg(e, (const void*)round, MP, 5, warp_bytes(MP, code.N, code.K), &kr);
+            if (rc) return rc;
+            const long long rgroups = (nf + fpw - 1) / fpw;
+            const long long rwant = (rgroups + kr.wpc - 1) / kr.wpc;
+            const int rgrid = (int)std::max<long long>(1, std::min<long long>(rwant, (long long)e->sms * kr.ctas_per_sm));
+            for (int r = 0; r < a.retries; ++r) {
+                SweepArgs q = p;
+                q.q_in = e->d_q[r & 1];
+                q.q_in_count = e->d_q_counts + r;
+                q.q_out = e->d_q[(r + 1) & 1];
+                q.q_out_count = e->d_q_counts + r + 1;
+                round<<<rgrid, kr.wpc * 32, kr.smem, st>>>(code, e->tb, q);
+                CUDA_TRY(cudaGetLastError());
+            }
+        }
+    }
+    return PB200_OK;
+}
+
+static void span_mask(const pb200_engine* e, int span, uint32_t* mask) {
+    for (int w = 0; w < kMaxWords; ++w) mask[w] = 0;
+    for (int j = 0; j < span && j < e->code.K; ++j) mask[e->info_pos[j] >> 5] |= 1u << (e->info_pos[j] & 31);
+}
+
+extern "C" int pb200_sweep(pb200_engine* e, const pb200_sweep_cfg* c, const float* d_beta, int64_t* d_counters,
+                           uint8_t* d_frame_bit_errors, uint8_t* d_frame_work, void* stream) {
+    int rc = check_sweep_cfg(e, c);
+    if (rc) return rc;
+    if (!d_counters) return fail(PB200_EINVAL, "counters is NULL");
+    if (c->n_frames == 0) return PB200_OK;
+    CUDA_TRY(cudaSetDevice(e->device));
+    SweepArgs a{};
+    a.llr = nullptr; a.in_len = 0;
+    a.frame_begin = c->frame_begin; a.n_frames = c->n_frames;
+    fill_chan(e, c, &a.cc);
+    a.retries = c->retries; a.run_scl = c->run_scl; a.fe_mode = c->frame_error_mode;
+    span_mask(e, c->bit_error_span, a.be_mask);
+    a.beta = d_beta;
+    a.counters = reinterpret_cast<unsigned long long*>(d_counters);
+    a.frame_bit_errors = d_frame_bit_errors;
+    a.frame_work = d_frame_work;
+    a.R = std::max(c->retries, 1);
+    return run_sweep(e, c->M, a, (cudaStream_t)stream);
+}
+
+extern "C" int pb200_dlscl_decode_batch(pb200_engine* e, const float* llr, int64_t B, int in_len, int M, int retries,
+                                        const float* d_beta, const pb200_dl_out* out, void* stream) {
+    int rc = check_decode_args(e, llr, B, in_len, M);
+    if (rc) return rc;
+    if (!out) return fail(PB200_EINVAL, "out is NULL");
+    if (B == 0) return PB200_OK;
+    CUDA_TRY(cudaSetDevice(e->device));
+    SweepArgs a{};
+    a.llr = llr; a.in_len = in_len;
+    a.frame_begin = 0; a.n_frames = B;
+    a.cc = ChanCfg{};
+    a.retries = std::max(retries, 0); a.run_scl = 0; a.fe_mode = 0;
+    span_mask(e, e->code.K, a.be_mask);
+    a.beta = d_beta;
+    a.counters = nullptr;
+    a.best_bits = out->best_bits; a.best_words = out->best_words; a.success = out->success;
+    a.n_attempts = out->n_attempts; a.tried = out->tried; a.flags = out->flags;
+    a.R = std::max(retries, 1);
+    return run_sweep(e, M, a, (cudaStream_t)stream);
+}
+
+extern "C" int pb200_channel_batch(pb200_engine* e, const pb200_sweep_cfg* c, uint8_t* d_msg, float* d_llr, void* stream) {
+    int rc = check_sweep_cfg(e, c);
+    if (rc) return rc;
+    if (c->n_frames == 0) return PB200_OK;
+    if (!d_llr) return fail(PB200_EINVAL, "llr is NULL");
+    CUDA_TRY(cudaSetDevice(e->device));
+    SweepArgs a{};
+    a.frame_begin = c->frame_begin; a.n_frames = c->n_frames;
+    fill_chan(e, c, &a.cc);
+    a.cc.include_uncoded = 0;
+    const size_t wb = WarpMem<4>::bytes(e->code.N);
+    const int wpc = 4;
+    const long long groups = (c->n_frames + 7) / 8;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((groups + wpc - 1) / wpc, (long long)e->sms * 8));
+    if (e->code.n <= 7) {
+        CUDA_TRY(cudaFuncSetAttribute(channel_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wb * wpc)));
+        channel_kernel<7><<<grid, wpc * 32, wb * wpc, (cudaStream_t)stream>>>(e->code, e->tb, a, d_msg, d_llr);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(channel_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wb * wpc)));
+        channel_kernel<9><<<grid, wpc * 32, wb * wpc, (cudaStream_t)stream>>>(e->code, e->tb, a, d_msg, d_llr);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return PB200_OK;
+}
+
+extern "C" int pb200_choose_flip_index_batch(const float* abs_l0, const float* beta, int32_t* idx, int64_t B, int K, void* stream) {
+    if (K <= 0) return fail(PB200_EINVAL, "abs_l0 cannot be empty");
+    if (B < 0) return fail(PB200_EINVAL, "bad B");
+    if (B == 0) return PB200_OK;
+    if (!abs_l0 || !idx) return fail(PB200_EINVAL, "NULL buffer");
+    if (K > 4096) return fail(PB200_ENOSUP, "K > 4096");
+    flip_index_kernel<<<(unsigned)B, 128, (size_t)K * sizeof(double), (cudaStream_t)stream>>>(abs_l0, beta, idx, K);
+    CUDA_TRY(cudaGetLastError());
+    return PB200_OK;
+}
+
+extern "C" int pb200_nr_encode_batch(pb200_engine* e, const uint8_t* payload, int8_t* tx, int64_t B, int E, void* stream) {
+    if (!e) return fail(PB200_EINVAL, "engine is NULL");
+    if (e->tb.E == 0 || E != e->tb.E) return fail(PB200_EINVAL, "call pb200_set_rate_matching(E) first");
+    if (e->code.crc_deg == 0) return fail(PB200_EINVAL, "NR encode needs a CRC polynomial");
+    if (B < 0) return fail(PB200_EINVAL, "bad B");
+    if (B == 0) return PB200_OK;
+    if (!payload || !tx) return fail(PB200_EINVAL, "NULL buffer");
+    CUDA_TRY(cudaSetDevice(e->device));
+    pb200_sweep_cfg c{};
+    c.noise_var = 1.0; c.noise_var_uncoded = 1.0;
+    c.k_payload = e->code.K - e->code.crc_deg;
+    ChanCfg cc;
+    fill_chan(e, &c, &cc);
+    nr_encode_kernel<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(e->code, e->tb, cc, payload, tx, B, E);
+    CUDA_TRY(cudaGetLastError());
+    return PB200_OK;
+}

@@ -72,20 +72,20 @@ template <int MP>
 struct WarpMem {
     float* tree;          // [(2^n - 2)][32]   heights 1..n-1, lane-interleaved
     float* chan;          // [FPW][N+1]        channel LLRs (height n), shared by the MP paths of a frame
-    unsigned long long* xchg;  // [32][2]      candidate keys for the rank exchange
+    unsigned long long* xchg;  // [32][2]      candidate keys for the rank exchange / small per-frame scratch
+    float* absl;          // [FPW][xk+1]       DL-SCL only: |L0| of the reference path (flip.py:102)
     static constexpr int FPW = 32 / MP;
-    __host__ __device__ static size_t bytes(int N) {
-        size_t t = (size_t)(N >= 4 ? N - 2 : 2) * 32 * 4;
-        size_t c = (size_t)FPW * (N + 1) * 4;
-        c = (c + 15) & ~(size_t)15;
-        return t + c + 32 * 16;
+    __host__ __device__ static size_t tree_bytes(int N) { return (size_t)(N >= 6 ? N - 2 : 4) * 32 * 4; }
+    __host__ __device__ static size_t chan_bytes(int N) { return ((size_t)FPW * (N + 1) * 4 + 15) & ~(size_t)15; }
+    __host__ __device__ static size_t bytes(int N, int xk = 0) {
+        size_t x = xk ? (((size_t)FPW * (xk + 1) * 4 + 15) & ~(size_t)15) : 0;
+        return tree_bytes(N) + chan_bytes(N) + 32 * 16 + x;
     }
     __device__ void carve(unsigned char* base, int N) {
-        size_t t = (size_t)(N >= 4 ? N - 2 : 2) * 32 * 4;
-        size_t c = ((size_t)FPW * (N + 1) * 4 + 15) & ~(size_t)15;
         tree = reinterpret_cast<float*>(base);
-        chan = reinterpret_cast<float*>(base + t);
-        xchg = reinterpret_cast<unsigned long long*>(base + t + c);
+        chan = reinterpret_cast<float*>(base + tree_bytes(N));
+        xchg = reinterpret_cast<unsigned long long*>(base + tree_bytes(N) + chan_bytes(N));
+        absl = reinterpret_cast<float*>(base + tree_bytes(N) + chan_bytes(N) + 32 * 16);
     }
 };
 

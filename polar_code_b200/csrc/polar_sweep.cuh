@@ -1,0 +1,670 @@
+// polar_sweep.cuh -- channel generation (Philox4x32-10 + Box-Muller), the fused Monte-Carlo sweep kernel and
+// DL-SCL flip retries as queue-compacted rounds.
+//
+// Reference paths: eval/run_fer_sweep.py:60-121 (channel, counters), eval/run_ber_sweep.py:112-181,
+// dlscl/flip.py:65-141 (retry controller), nr/polar/scl_nr.py:23-57 (rate-matched chain).
+//
+// DL-SCL on the GPU: the baseline pass decodes every frame; frames whose best path fails the CRC are appended
+// to a queue (frame id, best u-hat, tried set).  Each retry round is one launch over the compacted queue:
+// regenerate (Philox) or reload the frame's LLRs, replay the reference path to get |L0| (flip.py:102,133),
+// score q = |L0| @ beta in fp64 (flip.py:104-108), force the prefix + flipped bit (flip.py:30-34), decode, and
+// either finish the frame or append it to the next round's queue.  All lanes stay busy whatever the SNR.
+#pragma once
+#include "polar_kernels.cuh"
+
+namespace pb {
+
+// ---------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  counter = (frame_lo, frame_hi, block, purpose), key = (k0, k1).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+enum { kPurposePayload = 0, kPurposeNoise = 1, kPurposeUncoded = 2 };
+
+// four N(0,1) samples from one Philox block (two Box-Muller pairs)
+__device__ __forceinline__ void normal4(uint4 r, float (&z)[4]) {
+    const float u1 = fmaf((float)r.x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (x+0.5)/2^32 in (0,1]
+    const float u3 = fmaf((float)r.z, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float r1 = sqrtf(-2.0f * logf(u1)), r2 = sqrtf(-2.0f * logf(u3));
+    float s, c;
+    sincospif((float)r.y * 4.6566128730773926e-10f, &s, &c);  // 2*pi*u2, u2 = y/2^32
+    z[0] = r1 * c; z[1] = r1 * s;
+    sincospif((float)r.w * 4.6566128730773926e-10f, &s, &c);
+    z[2] = r2 * c; z[3] = r2 * s;
+}
+
+struct ChanCfg {
+    uint32_t k0, k1;           // Philox key (seed, stream)
+    float sigma, scale;        // noise sigma, 2/sigma^2
+    float sigma_u, scale_u;    // uncoded branch
+    int kp;                    // payload bits (K - kp CRC bits attached)
+    int include_uncoded;
+    unsigned long long poly;   // CRC polynomial incl. leading 1
+    int deg;
+    const int16_t* tx_src;     // [E] NR transmit gather (code index or -1 = pad symbol +3)
+    const int16_t* rm_dst;     // [N] NR: internal index fed by de-rate-matched position p (-1 none)
+};
+
+struct DlEntryHdr { long long frame; uint32_t flags; uint32_t n_tried; };
+
+struct SweepArgs {
+    // source: llr != null -> LLR-in mode (rows indexed by frame), else Philox channel
+    const float* llr;
+    int in_len;
+    long long frame_begin, n_frames;
+    ChanCfg cc;
+    int retries, run_scl, fe_mode;
+    uint32_t be_mask[kMaxWords];   // phases whose bits are compared for bit errors
+    const float* beta;
+    unsigned long long* counters;
+    uint8_t* frame_bit_errors;
+    uint8_t* frame_work;
+    // DL API outputs (indexed by frame - frame_begin)
+    uint8_t* best_bits;
+    uint32_t* best_words;
+    uint8_t* success;
+    int32_t* n_attempts;
+    int32_t* tried;
+    int R;
+    uint32_t* flags;
+    // retry queues: entry = hdr + u[XW] + tried[XW]
+    unsigned char* q_in;
+    unsigned char* q_out;
+    unsigned int* q_in_count;
+    unsigned int* q_out_count;
+    unsigned int q_capacity;
+};
+
+template <int XW> struct DlEntry { DlEntryHdr h; uint32_t u[XW]; uint32_t tried[XW]; };
+
+// counters indices (include/polar_b200.h)
+enum { cFrames = 0, cSclFe, cSclBe, cDlFe, cDlBe, cUncFe, cUncBe, cDlWork, cNearTie, cSclUndet, cDlUndet, cRankTie, cNum };
+
+// ---------------------------------------------------------------------------------------------------
+// Channel generation for the FPW frames of a warp.  `my_frame` = global frame index of this lane's group (<0 none).
+// Leaves the channel LLRs in wm.chan, returns the transmitted u (all lanes of the group) and the frame's uncoded
+// bit-error count.  Scratch: the (not yet used) tree area.
+// ---------------------------------------------------------------------------------------------------
+template <int MP, int XW>
+__device__ __forceinline__ void gen_channel(const Code& code, const Tables& tb, const ChanCfg& cc, const WarpMem<MP>& wm,
+                                            long long my_frame, int lane, uint32_t (&u_sent)[XW], uint32_t& unc_err,
+                                            bool want_chan, float* raw_out = nullptr, long long raw_base = 0) {
+    constexpr int FPW = 32 / MP;
+    const int N = code.N, K = code.K;
+    const int xwn = N >= 32 ? N / 32 : 1;
+    const int slot = lane & (MP - 1), gbase = lane & ~(MP - 1), fme = lane / MP;
+    uint32_t* scr = reinterpret_cast<uint32_t*>(wm.tree);      // per-lane column: scr[w*32 + lane]
+    const uint2 key = make_uint2(cc.k0, cc.k1);
+    const int pwn = (cc.kp + 31) / 32;
+    // ---- payload -> CRC -> u -> x on the group leader ------------------------------------------------
+    // scratch rows of the leader's column: payload [0,xwn), message [xwn,2xwn), u / codeword [2xwn,3xwn)
+    const int R1 = xwn, R2 = 2 * xwn;
+    if (slot == 0 && my_frame >= 0) {
+        for (int w = 0; w < xwn; ++w) { scr[w * 32 + lane] = 0; scr[(R1 + w) * 32 + lane] = 0; scr[(R2 + w) * 32 + lane] = 0; }
+        for (int w = 0; w < pwn; w += 4) {
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)my_frame, (uint32_t)(my_frame >> 32), (uint32_t)(w >> 2), kPurposePayload), key);
+            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (w + c < pwn) {
+                    uint32_t v = rr[c];
+                    const int rem = cc.kp - (w + c) * 32;
+                    if (rem < 32) v &= (1u << rem) - 1u;
+                    scr[(w + c) * 32 + lane] = v;
+                    scr[(R1 + w + c) * 32 + lane] = v;
+                }
+            }
+        }
+        // attach_crc (crc.py:19-37): remainder of payload(x) x^deg, appended MSB first
+        if (cc.kp < K) {
+            const unsigned long long low = cc.poly & ((1ull << cc.deg) - 1ull);
+            unsigned long long reg = 0;
+            for (int j = 0; j < cc.kp; ++j) {
+                const unsigned long long b = (scr[(j >> 5) * 32 + lane] >> (j & 31)) & 1u;
+                const unsigned long long top = ((reg >> (cc.deg - 1)) & 1ull) ^ b;
+                reg = (reg << 1) & ((1ull << cc.deg) - 1ull);
+                if (top) reg ^= low;
+            }
+            for (int t = 0; t < cc.deg && cc.kp + t < K; ++t) {
+                const int j = cc.kp + t;
+                const uint32_t b = (uint32_t)((reg >> (cc.deg - 1 - t)) & 1ull);
+                scr[(R1 + (j >> 5)) * 32 + lane] |= b << (j & 31);
+            }
+        }
+        // u[A] = msg (polar.py:116-117)
+        for (int j = 0; j < K; ++j) {
+            const uint32_t b = (scr[(R1 + (j >> 5)) * 32 + lane] >> (j & 31)) & 1u;
+            const int pos = __ldg(&tb.info_pos[j]);
+            scr[(R2 + (pos >> 5)) * 32 + lane] |= b << (pos & 31);
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int w = 0; w < XW; ++w) u_sent[w] = (w < xwn) ? scr[(R2 + w) * 32 + gbase] : 0u;
+    uint32_t x[XW];
+#pragma unroll
+    for (int w = 0; w < XW; ++w) x[w] = u_sent[w];
+    transform_words<XW>(x, code.n);                           // codeword (polar.py:118)
+    __syncwarp();
+    // codeword words -> rows 2XW.. of the leader column so any lane can read any frame's bits
+    if (slot == 0) {
+#pragma unroll
+        for (int w = 0; w < XW; ++w) if (w < xwn) scr[(R2 + w) * 32 + lane] = x[w];
+    }
+    __syncwarp();
+    unc_err = 0;
+    // frame ids of all groups, staged in smem so the item loops below can address any frame
+    long long* fids = reinterpret_cast<long long*>(wm.xchg + 16);     // xchg has 64 u64; use the upper half
+    if (slot == 0) fids[fme] = my_frame;
+    __syncwarp();
+    // ---- uncoded BPSK reference (run_fer_sweep.py:111-121) --------------------------------------------
+    if (cc.include_uncoded) {
+        uint32_t* cnt = reinterpret_cast<uint32_t*>(wm.xchg);
+        if (lane < FPW) cnt[lane] = 0;
+        __syncwarp();
+        const int nblk = (cc.kp + 3) / 4;
+        for (int item = lane; item < FPW * nblk; item += 32) {
+            const int f = item / nblk, jb = item - f * nblk;
+            const long long fr = fids[f];
+            if (fr < 0) continue;
+            float z[4];
+            normal4(philox4x32_10(make_uint4((uint32_t)fr, (uint32_t)(fr >> 32), (uint32_t)jb, kPurposeUncoded), key), z);
+            uint32_t err = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int j = jb * 4 + c;
+                if (j < cc.kp) {
+                    const uint32_t b = (scr[(j >> 5) * 32 + f * MP] >> (j & 31)) & 1u;
+                    const float y = fmaf(cc.sigma_u, z[c], 1.0f - 2.0f * (float)b);
+                    err += (uint32_t)((y * cc.scale_u < 0.f) ? 1u : 0u) ^ b;
+                }
+            }
+            if (err) atomicAdd(&cnt[f], err);
+        }
+        __syncwarp();
+        unc_err = cnt[fme];
+        __syncwarp();
+    }
+    if (!want_chan) return;
+    // ---- coded channel: BPSK + AWGN -> LLR (run_fer_sweep.py:83-87), NR chain fused (scl_nr.py:31-35,47-48) --
+    const bool nr = tb.E != 0;
+    const int Eeff = nr ? tb.E : N;
+    const int nblk = N >= 4 ? N / 4 : 1;
+    if (nr && !raw_out) {
+        for (int e = lane; e < FPW * N; e += 32) wm.chan[(e >> code.n) * (N + 1) + (e & (N - 1))] = 0.f;
+        __syncwarp();
+    }
+    const int rounds = (Eeff + N - 1) / N;
+    for (int k = 0; k < rounds; ++k) {
+        for (int item = lane; item < FPW * nblk; item += 32) {
+            const int f = item / nblk, jb = item - f * nblk;
+            const long long fr = fids[f];
+            if (fr < 0) continue;
+            float z[4];
+            normal4(philox4x32_10(make_uint4((uint32_t)fr, (uint32_t)(fr >> 32), (uint32_t)(k * nblk + jb), kPurposeNoise), key), z);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int p = jb * 4 + c;          // position inside this round
+                const int t = k * N + p;           // transmitted position
+                if (p < N && t < Eeff) {
+                    const int src = nr ? (int)__ldg(&cc.tx_src[t]) : t;
+                    float s = 3.0f;                // BPSK of the interleaver pad value -1 (interleaver.py:17)
+                    if (src >= 0) s = 1.0f - 2.0f * (float)((scr[(R2 + (src >> 5)) * 32 + f * MP] >> (src & 31)) & 1u);
+                    const float llr = fmaf(cc.sigma, z[c], s) * cc.scale;
+                    if (raw_out) raw_out[(fr - raw_base) * (long long)Eeff + t] = llr;
+                    else if (!nr) wm.chan[f * (N + 1) + t] = llr;
+                    else {
+                        const int dst = __ldg(&cc.rm_dst[p]);
+                        if (dst >= 0) wm.chan[f * (N + 1) + dst] += llr;   // k ascending = the order of load_channel
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (nr && !raw_out) {
+        for (int e = lane; e < FPW * N; e += 32) {
+            const int f = e >> code.n, i = e & (N - 1);
+            const int p = tb.rm_src[i];
+            float v = 0.f;
+            if (p >= 0) {
+                const int cnt = p < Eeff ? (Eeff - p + N - 1) / N : 0;
+                v = cnt ? wm.chan[f * (N + 1) + i] / (float)cnt : -1.0f;
+            }
+            wm.chan[f * (N + 1) + i] = v;
+        }
+        __syncwarp();
+    }
+}
+
+
+// Gather-load of channel LLRs for arbitrary frame ids (LLR-in mode of the DL-SCL rounds).
+template <int MP>
+__device__ __forceinline__ void load_channel_ids(const Code& code, const Tables& tb, const WarpMem<MP>& wm, const float* llr,
+                                                 int in_len, long long my_frame, long long frame_begin, int lane) {
+    constexpr int FPW = 32 / MP;
+    const int N = code.N;
+    long long* fids = reinterpret_cast<long long*>(wm.xchg + 16);
+    if ((lane & (MP - 1)) == 0) fids[lane / MP] = my_frame;
+    __syncwarp();
+    for (int e = lane; e < FPW * N; e += 32) {
+        const int f = e >> code.n, i = e & (N - 1);
+        const long long fr = fids[f];
+        float v = 0.f;
+        if (fr >= 0) {
+            const float* row = llr + (fr - frame_begin) * (long long)in_len;
+            if (tb.E == 0) v = row[i];
+            else {
+                const int p = tb.rm_src[i];
+                if (p >= 0) {
+                    float acc = 0.f;
+                    int cnt = 0;
+                    for (int q = p; q < tb.E; q += N) { acc += row[q]; ++cnt; }
+                    v = cnt ? acc / (float)cnt : -1.0f;
+                }
+            }
+        }
+        wm.chan[f * (N + 1) + i] = v;
+    }
+    __syncwarp();
+}
+
+template <int MP, int LOGMAX>
+struct Sweep {
+    using DecU = ListDecoder<MP, LOGMAX, false, true>;
+    using DecF = ListDecoder<MP, LOGMAX, true, true>;
+    using PathT = Path<LOGMAX>;
+    static constexpr int XW = PathT::XW;
+    static constexpr int FPW = 32 / MP;
+    static constexpr uint32_t GM = DecU::GM;
+    using Entry = DlEntry<XW>;
+
+    struct Best { uint32_t u[XW]; bool pass; uint32_t flags; };   // identical on all lanes of a group
+
+    // best candidate of a finished list decode (scl.py:183-197), broadcast to the group
+    static __device__ __forceinline__ void pick_best(const Code& code, const Tables& tb, const PathT& p, int lane, uint32_t flags, Best& b) {
+        const int gbase = lane & ~(MP - 1);
+        uint32_t u[XW];
+#pragma unroll
+        for (int k = 0; k < XW; ++k) u[k] = p.alive ? p.xh[k] : 0u;
+        transform_words<XW>(u, code.n);
+        const bool pass = p.alive && (code.crc_deg == 0 || crc_syndrome<XW>(code, tb, u) == 0);
+        uint32_t v = (pass && code.crc_deg > 0) ? p.r : 0xffu;
+#pragma unroll
+        for (int o = 1; o < MP; o <<= 1) v = min(v, __shfl_xor_sync(kFull, v, o));
+        const uint32_t best_r = (v == 0xffu) ? 0u : v;
+        const uint32_t bm = (__ballot_sync(kFull, p.alive && p.r == best_r) >> gbase) & GM;
+        const int bl = gbase + (bm ? __ffs(bm) - 1 : 0);
+#pragma unroll
+        for (int k = 0; k < XW; ++k) b.u[k] = __shfl_sync(kFull, u[k], bl);
+        b.pass = __shfl_sync(kFull, (int)pass, bl) != 0;
+#pragma unroll
+        for (int o = 1; o < MP; o <<= 1) flags |= __shfl_xor_sync(kFull, flags, o);
+        b.flags = flags;
+    }
+
+    static __device__ __forceinline__ uint32_t bit_errors(const Code& code, const SweepArgs& a, const Best& b, const uint32_t (&u_sent)[XW], bool& wrong) {
+        uint32_t e = 0, d = 0;
+#pragma unroll
+        for (int w = 0; w < XW; ++w) {
+            const uint32_t x = (b.u[w] ^ u_sent[w]) & code.info_mask[w];
+            d |= x;
+            e += __popc(x & a.be_mask[w]);
+        }
+        wrong = d != 0;
+        return e;
+    }
+
+    // write the per-frame results of a finished DL-SCL frame (flip.py:137-141) / count it (run_fer_sweep.py:100-109)
+    static __device__ __forceinline__ void finish_dl(const Code& code, const Tables& tb, const SweepArgs& a, const WarpMem<MP>& wm, int lane,
+                                                     long long frame, const Best& b, uint32_t n_tried, const uint32_t (&u_sent)[XW], uint32_t (&acc)[cNum]) {
+        const long long idx = frame - a.frame_begin;
+        if (a.llr == nullptr) {
+            bool wrong;
+            const uint32_t be = bit_errors(code, a, b, u_sent, wrong);
+            acc[cDlBe] += be;
+            acc[cDlFe] += (a.fe_mode == 0) ? (b.pass ? 0u : 1u) : (be ? 1u : 0u);
+            acc[cDlUndet] += (b.pass && wrong) ? 1u : 0u;
+            acc[cDlWork] += n_tried;
+            if (a.frame_bit_errors) a.frame_bit_errors[idx] = (uint8_t)min(be, 255u);
+            if (a.frame_work) a.frame_work[idx] = (uint8_t)min(n_tried, 255u);
+        }
+        acc[cRankTie] += (b.flags & PB_FLAG_RANK_TIE) ? 1u : 0u;
+        const int xwn = code.N >= 32 ? code.N / 32 : 1;
+        if (a.best_words) for (int k = 0; k < xwn; ++k) { uint32_t w = 0;
+#pragma unroll
+            for (int q = 0; q < XW; ++q) if (q == k) w = b.u[q];
+            a.best_words[idx * xwn + k] = w; }
+        if (a.best_bits) {
+            float* stash = wm.tree + lane;
+#pragma unroll
+            for (int k = 0; k < XW; ++k) if (k < xwn) stash[k * 32] = __uint_as_float(b.u[k]);
+            write_info_bits(code, tb, stash, a.best_bits + idx * (long long)code.K);
+        }
+        if (a.success) a.success[idx] = (uint8_t)b.pass;
+        if (a.n_attempts) a.n_attempts[idx] = (int32_t)(1 + n_tried);
+        if (a.flags) a.flags[idx] = b.flags;
+    }
+
+    // warp-aggregated append of the leaders with `need` to the output queue
+    static __device__ __forceinline__ void enqueue(const SweepArgs& a, int lane, bool need, long long frame, const Best& b,
+                                                   const uint32_t (&tried)[XW], uint32_t n_tried) {
+        const uint32_t m = __ballot_sync(kFull, need);
+        if (m == 0) return;
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(a.q_out_count, (unsigned int)__popc(m));
+        base = __shfl_sync(kFull, base, 0);
+        if (need) {
+            const unsigned int slot = base + __popc(m & ((1u << lane) - 1u));
+            if (slot < a.q_capacity) {
+                Entry* e = reinterpret_cast<Entry*>(a.q_out) + slot;
+                e->h.frame = frame; e->h.flags = b.flags; e->h.n_tried = n_tried;
+#pragma unroll
+                for (int k = 0; k < XW; ++k) { e->u[k] = b.u[k]; e->tried[k] = tried[k]; }
+            }
+        }
+    }
+
+    static __device__ __forceinline__ void flush(const SweepArgs& a, int lane, uint32_t (&acc)[cNum]) {
+        if (a.counters == nullptr) return;
+#pragma unroll
+        for (int c = 0; c < cNum; ++c) {
+            const uint32_t s = __reduce_add_sync(kFull, acc[c]);
+            if (lane == 0 && s) atomicAdd(&a.counters[c], (unsigned long long)s);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Baseline pass: channel -> SCL(M) -> counters; failing frames go to the retry queue.
+// ---------------------------------------------------------------------------------------------------
+template <int MP, int LOGMAX>
+__global__ void sweep_kernel(const Code code, const Tables tb, const SweepArgs a) {
+    using S = Sweep<MP, LOGMAX>;
+    using PathT = typename S::PathT;
+    constexpr int FPW = 32 / MP, XW = S::XW;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    WarpMem<MP> wm;
+    wm.carve(smem + (size_t)warp * WarpMem<MP>::bytes(code.N), code.N);
+    const bool leader = (lane & (MP - 1)) == 0;
+    uint32_t acc[cNum];
+#pragma unroll
+    for (int c = 0; c < cNum; ++c) acc[c] = 0;
+    const long long ngroups = (a.n_frames + FPW - 1) / FPW;
+    for (long long g = (long long)blockIdx.x * wpc + warp; g < ngroups; g += (long long)gridDim.x * wpc) {
+        const long long idx = g * FPW + lane / MP;
+        const bool valid = idx < a.n_frames;
+        const long long my_frame = valid ? a.frame_begin + idx : -1;
+        uint32_t u_sent[XW];
+        uint32_t unc = 0;
+        if (a.llr) {
+#pragma unroll
+            for (int k = 0; k < XW; ++k) u_sent[k] = 0;
+            load_channel_ids<MP>(code, tb, wm, a.llr, a.in_len, my_frame, a.frame_begin, lane);
+        } else {
+            gen_channel<MP, XW>(code, tb, a.cc, wm, my_frame, lane, u_sent, unc, true);
+        }
+        uint32_t flags = 0;
+        uint32_t fm[XW], fv[XW];
+        PathT p;
+        S::DecU::init(p, lane, valid);
+        S::DecU::run(code, wm, p, lane, fm, fv, flags);
+        typename S::Best b;
+        S::pick_best(code, tb, p, lane, flags, b);
+        bool need = false;
+        uint32_t tried[XW];
+#pragma unroll
+        for (int k = 0; k < XW; ++k) tried[k] = 0;
+        if (leader && valid) {
+            acc[cFrames] += 1;
+            acc[cNearTie] += (b.flags & PB_FLAG_NEAR_TIE) ? 1u : 0u;
+            if (a.llr == nullptr) {
+                bool wrong;
+                const uint32_t be = S::bit_errors(code, a, b, u_sent, wrong);
+                if (a.run_scl) {
+                    acc[cSclBe] += be;
+                    acc[cSclFe] += (a.fe_mode == 0) ? (b.pass ? 0u : 1u) : (be ? 1u : 0u);
+                    acc[cSclUndet] += (b.pass && wrong) ? 1u : 0u;
+                }
+                if (a.cc.include_uncoded) { acc[cUncBe] += unc; acc[cUncFe] += unc ? 1u : 0u; }
+                if (a.retries < 0) {
+                    if (a.frame_bit_errors) a.frame_bit_errors[idx] = (uint8_t)min(be, 255u);
+                    if (a.frame_work) a.frame_work[idx] = 0;
+                }
+            }
+            if (a.retries >= 0) {
+                const bool pass = code.crc_deg == 0 ? true : b.pass;       // flip.py:82-88 _passes
+                need = !(pass || a.retries == 0);                          // flip.py:90
+            }
+        }
+        if (a.retries >= 0) {
+            if (leader && valid && !need) S::finish_dl(code, tb, a, wm, lane, my_frame, b, 0, u_sent, acc);
+            S::enqueue(a, lane, need, my_frame, b, tried, 0);
+        }
+        __syncwarp();
+    }
+    S::flush(a, lane, acc);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// One DL-SCL retry round over the compacted queue (flip.py:110-135).
+// ---------------------------------------------------------------------------------------------------
+template <int MP, int LOGMAX>
+__global__ void dl_round_kernel(const Code code, const Tables tb, const SweepArgs a) {
+    using S = Sweep<MP, LOGMAX>;
+    using PathT = typename S::PathT;
+    using Entry = typename S::Entry;
+    constexpr int FPW = 32 / MP, XW = S::XW;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    WarpMem<MP> wm;
+    wm.carve(smem + (size_t)warp * WarpMem<MP>::bytes(code.N, code.K), code.N);
+    const int slot = lane & (MP - 1), fme = lane / MP;
+    const bool leader = slot == 0;
+    const int K = code.K;
+    uint32_t acc[cNum];
+#pragma unroll
+    for (int c = 0; c < cNum; ++c) acc[c] = 0;
+    const unsigned int n_in = min(*a.q_in_count, a.q_capacity);
+    const long long ngroups = ((long long)n_in + FPW - 1) / FPW;
+    for (long long g = (long long)blockIdx.x * wpc + warp; g < ngroups; g += (long long)gridDim.x * wpc) {
+        const long long idx = g * FPW + fme;
+        const bool valid = idx < (long long)n_in;
+        long long my_frame = -1;
+        uint32_t eflags = 0, n_tried = 0;
+        uint32_t u_ref[XW], tried[XW];
+#pragma unroll
+        for (int k = 0; k < XW; ++k) { u_ref[k] = 0; tried[k] = 0; }
+        if (valid) {
+            const Entry* e = reinterpret_cast<const Entry*>(a.q_in) + idx;
+            my_frame = e->h.frame; eflags = e->h.flags; n_tried = e->h.n_tried;
+#pragma unroll
+            for (int k = 0; k < XW; ++k) { u_ref[k] = e->u[k]; tried[k] = e->tried[k]; }
+        }
+        uint32_t u_sent[XW];
+        uint32_t unc = 0;
+        if (a.llr) {
+#pragma unroll
+            for (int k = 0; k < XW; ++k) u_sent[k] = 0;
+            load_channel_ids<MP>(code, tb, wm, a.llr, a.in_len, my_frame, a.frame_begin, lane);
+        } else {
+            ChanCfg cc = a.cc;
+            cc.include_uncoded = 0;
+            gen_channel<MP, XW>(code, tb, cc, wm, my_frame, lane, u_sent, unc, true);
+        }
+        // |L0| of the reference path (flip.py:102,133): replay it and keep the info-phase leaf LLRs
+        float* ab = wm.absl + fme * (K + 1);
+        S::DecU::replay(code, wm, lane, valid, u_ref, [&](int j, float L) { if (leader) ab[j] = fabsf(L); });
+        __syncwarp();
+        // rank_indices (flip.py:104-108): first untried index of argsort(|L0| @ beta) = argmin over untried
+        double m1 = 1e300, m2 = 1e300;
+        int a1 = 0x7fffffff;
+#pragma unroll
+        for (int w = 0; w < XW; ++w) {
+            if (w * 32 < K) {
+                double q[32 / MP];
+#pragma unroll
+                for (int k = 0; k < 32 / MP; ++k) q[k] = 0.0;
+                if (a.beta) {
+                    for (int i = 0; i < K; ++i) {
+                        const double x = (double)ab[i];
+#pragma unroll
+                        for (int k = 0; k < 32 / MP; ++k) {
+                            const int j = w * 32 + slot + MP * k;
+                            if (j < K) q[k] += x * (double)__ldg(&a.beta[(size_t)i * K + j]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 32 / MP; ++k) {
+                        const int j = w * 32 + slot + MP * k;
+                        if (j < K) q[k] = (double)ab[j];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 32 / MP; ++k) {
+                    const int jj = slot + MP * k, j = w * 32 + jj;
+                    if (j < K && !((tried[w] >> jj) & 1u)) {
+                        if (q[k] < m1 || (q[k] == m1 && j < a1)) { m2 = m1; m1 = q[k]; a1 = j; }
+                        else if (q[k] < m2) m2 = q[k];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 1; o < MP; o <<= 1) {
+            const double om1 = __shfl_xor_sync(kFull, m1, o), om2 = __shfl_xor_sync(kFull, m2, o);
+            const int oa1 = __shfl_xor_sync(kFull, a1, o);
+            if (om1 < m1 || (om1 == m1 && oa1 < a1)) { m2 = fmin(m1, om2); m1 = om1; a1 = oa1; }
+            else m2 = fmin(m2, om1);
+        }
+        const int jf = valid ? a1 : 0;
+        if (valid && m2 < 1e299 && (m2 - m1) <= 2e-6 * fmax(fabs(m1), fabs(m2))) eflags |= PB_FLAG_RANK_TIE;
+        const int pf = (jf < K) ? (int)__ldg(&tb.info_pos[jf]) : 0;
+        // _force_vector (flip.py:30-34): prefix of the reference bits, then the flipped bit, rest free
+        uint32_t fm[XW], fv[XW];
+#pragma unroll
+        for (int w = 0; w < XW; ++w) {
+            const int lo = w * 32;
+            const uint32_t below = (pf >= lo + 32) ? 0xffffffffu : (pf <= lo ? 0u : ((1u << (pf - lo)) - 1u));
+            const uint32_t bit = (pf >= lo && pf < lo + 32) ? (1u << (pf - lo)) : 0u;
+            fm[w] = code.info_mask[w] & (below | bit);
+            fv[w] = (u_ref[w] & below) | (~u_ref[w] & bit);
+            if (jf >= lo && jf < lo + 32) tried[w] |= 1u << (jf - lo);      // tried set is indexed by info index
+        }
+        n_tried += 1;
+        if (leader && valid && a.tried) a.tried[(my_frame - a.frame_begin) * (long long)a.R + (n_tried - 1)] = jf;
+        uint32_t flags = 0;
+        PathT p;
+        S::DecF::init(p, lane, valid);
+        S::DecF::run(code, wm, p, lane, fm, fv, flags);        // retry_with_flip (flip.py:37-62)
+        typename S::Best b;
+        S::pick_best(code, tb, p, lane, flags | eflags, b);
+        bool need = false;
+        if (leader && valid) {
+            acc[cNearTie] += ((b.flags & PB_FLAG_NEAR_TIE) && !(eflags & PB_FLAG_NEAR_TIE)) ? 1u : 0u;
+            const bool pass = code.crc_deg == 0 ? true : b.pass;
+            need = !(pass || (int)n_tried >= a.retries || (int)n_tried >= K);   // flip.py:111,134
+            if (!need) S::finish_dl(code, tb, a, wm, lane, my_frame, b, n_tried, u_sent, acc);
+        }
+        S::enqueue(a, lane, need, my_frame, b, tried, n_tried);
+        __syncwarp();
+    }
+    S::flush(a, lane, acc);
+}
+
+// Channel only: msg[B,K] u8 and raw LLRs [B, E or N] (same Philox stream as sweep_kernel).
+template <int LOGMAX>
+__global__ void channel_kernel(const Code code, const Tables tb, const SweepArgs a, uint8_t* msg, float* llr) {
+    constexpr int MP = 4, FPW = 8;
+    constexpr int XW = BitsCfg<LOGMAX>::XW;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    WarpMem<MP> wm;
+    wm.carve(smem + (size_t)warp * WarpMem<MP>::bytes(code.N), code.N);
+    const long long ngroups = (a.n_frames + FPW - 1) / FPW;
+    for (long long g = (long long)blockIdx.x * wpc + warp; g < ngroups; g += (long long)gridDim.x * wpc) {
+        const long long idx = g * FPW + lane / MP;
+        const bool valid = idx < a.n_frames;
+        const long long my_frame = valid ? a.frame_begin + idx : -1;
+        uint32_t u_sent[XW];
+        uint32_t unc;
+        gen_channel<MP, XW>(code, tb, a.cc, wm, my_frame, lane, u_sent, unc, true, llr, a.frame_begin);
+        if (msg && valid && (lane & (MP - 1)) == 0) {
+            float* stash = wm.tree + lane;
+            const int xwn = code.N >= 32 ? code.N / 32 : 1;
+#pragma unroll
+            for (int k = 0; k < XW; ++k) if (k < xwn) stash[k * 32] = __uint_as_float(u_sent[k]);
+            write_info_bits(code, tb, stash, msg + idx * (long long)code.K);
+        }
+        __syncwarp();
+    }
+}
+
+// choose_flip_index (flip.py:13-27): one block per row, argmin(abs_l0 @ beta) / argmin(abs_l0), first minimum.
+__global__ void flip_index_kernel(const float* __restrict__ abs_l0, const float* __restrict__ beta, int32_t* __restrict__ out, int K) {
+    extern __shared__ double qs[];
+    const long long row = blockIdx.x;
+    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+        double q = 0.0;
+        if (beta) for (int i = 0; i < K; ++i) q += (double)abs_l0[row * K + i] * (double)beta[(size_t)i * K + j];
+        else q = (double)abs_l0[row * K + j];
+        qs[j] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int best = 0;
+        for (int j = 1; j < K; ++j) if (qs[j] < qs[best]) best = j;
+        out[row] = best;
+    }
+}
+
+// encode_rate_matched (scl_nr.py:23-35): payload[B,Kp] -> CRC -> encode -> interleave -> rate-match; one thread per frame.
+__global__ void nr_encode_kernel(const Code code, const Tables tb, const ChanCfg cc, const uint8_t* __restrict__ payload, int8_t* __restrict__ tx,
+                                 long long B, int E) {
+    const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= B) return;
+    uint32_t u[kMaxWords];
+#pragma unroll
+    for (int k = 0; k < kMaxWords; ++k) u[k] = 0;
+    const unsigned long long low = cc.poly & ((1ull << cc.deg) - 1ull);
+    unsigned long long reg = 0;
+    auto put = [&](int j, uint32_t b) {
+        const int pos = tb.info_pos[j];
+#pragma unroll
+        for (int k = 0; k < kMaxWords; ++k) if (k == (pos >> 5)) u[k] |= b << (pos & 31);
+    };
+    for (int j = 0; j < cc.kp; ++j) {
+        const uint32_t b = payload[f * cc.kp + j] & 1u;
+        put(j, b);
+        const unsigned long long top = ((reg >> (cc.deg - 1)) & 1ull) ^ b;
+        reg = (reg << 1) & ((1ull << cc.deg) - 1ull);
+        if (top) reg ^= low;
+    }
+    if (cc.deg > 0) for (int t = 0; t < cc.deg && cc.kp + t < code.K; ++t) put(cc.kp + t, (uint32_t)((reg >> (cc.deg - 1 - t)) & 1ull));
+    transform_words<kMaxWords>(u, code.n);
+    for (int t = 0; t < E; ++t) {
+        const int src = cc.tx_src[t];
+        int8_t v = -1;
+        if (src >= 0) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int k = 0; k < kMaxWords; ++k) if (k == (src >> 5)) w = u[k];
+            v = (int8_t)((w >> (src & 31)) & 1u);
+        }
+        tx[f * E + t] = v;
+    }
+}
+
+}  // namespace pb
