@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: SCL M=4, P(128,64)+CRC-24 decoded frames/s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path (decode_scl, list size 4, CRC-24 selection) over one batch of synthetic
+AWGN frames spread evenly over the reference sweep's SNR grid 4.0 .. 6.5 dB (config[0] of BASELINE.json, run
+at a Monte-Carlo batch size).  `value` times the decode kernel with the LLRs already resident in HBM; `e2e`
+times the same decode through the host-buffer C-ABI call (pinned host LLRs in, decisions out, copies inside
+the timed region).  The reference arm (--impl reference) times the CPU path (the pinned C oracle, all host
+threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+CRC24 = "0x1864CFB"
+N, K, KP, M = 128, 64, 40, 4
+SNR_GRID = [4.0, 4.5, 5.0, 5.5, 6.0, 6.5]          # run_fer_sweep defaults (config.py:19, run_fer_sweep.py:198-200)
+METRIC = "SCL M=4 N=128 decoded frames/s"
+UNIT = "frames/s"
+# algorithmic work per frame (lazy SC schedule, golden info set)
+ELEM_OPS = {1: 1088, 2: 2023, 4: 3843, 8: 7439}
+HBM_BYTES_PER_FRAME = 4 * N + K + 1 + 4            # LLR row in, best_bits + crc_ok + flags out (u8 decisions)
+
+
+def noise_var(snr_db: float) -> float:
+    return 1.0 / (2.0 * (K / N) * 10 ** (snr_db / 10.0))   # run_fer_sweep.py:62-64
+
+
+def peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": float(d["hbm_gbs"]), "sm_max_mhz": float(d.get("sm_max_mhz", 1965.0)), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self) -> dict:
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(sample_frames: int, threads: int = 0) -> dict:
+    """Oracle port (oracle/polar_oracle.c, fp64, pthreads over frames) on a bounded sample of the workload."""
+    from oracle import oracle as O
+    A = O.construct_info_set(N, K)
+    rng = np.random.default_rng(12345)
+    per = sample_frames // len(SNR_GRID)
+    llrs = []
+    for s in SNR_GRID:
+        nv = noise_var(s)
+        payload = rng.integers(0, 2, (per, KP), dtype=np.int8)
+        msgs = np.array([O.attach_crc(p, CRC24) for p in payload[:256]])
+        reps = (per + 255) // 256
+        codes = np.tile(np.array([O.encode(m, A, N) for m in msgs]), (reps, 1))[:per]
+        llrs.append(2.0 * (1.0 - 2.0 * codes + rng.normal(0, np.sqrt(nv), codes.shape)) / nv)
+    llr = np.ascontiguousarray(np.concatenate(llrs))
+    nthreads = threads or O.lib().po_num_threads()
+    O.scl_decode_batch(llr[:2048], A, M, crc=CRC24, want_info_llrs=False, nthreads=nthreads)   # warm
+    t = time.perf_counter()
+    O.scl_decode_batch(llr, A, M, crc=CRC24, want_info_llrs=False, nthreads=nthreads)
+    dt = time.perf_counter() - t
+    return {"value": llr.shape[0] / dt, "unit": UNIT, "cores": int(nthreads), "kind": "port",
+            "sample": f"{llr.shape[0]} frames (SNR grid 4.0-6.5 dB), decode_scl M=4 + CRC-24, float64 C oracle, {dt:.2f} s wall"}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = args.steps, args.warmup
+    sample = args.cpu_sample
+    for _ in range(max(warm, 1) - 1):
+        cpu_baseline(sample // 8)
+    vals = [cpu_baseline(sample) for _ in range(max(steps, 1))]
+    v = float(np.mean([x["value"] for x in vals]))
+    cb = dict(vals[-1])
+    cb["value"] = v
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": 1e3 * sample / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(sample, args.gpus, cpu=True),
+        "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(frames_per_step: int, gpus: int, cpu: bool = False) -> dict:
+    return {"workload": "decode_scl M=4 + CRC-24A selection on P(128,64) (40 payload + 24 CRC), AWGN BPSK LLRs, "
+                        "frames spread evenly over Eb/N0 4.0-6.5 dB step 0.5 (BASELINE configs[0] geometry at Monte-Carlo batch size)",
+            "N": N, "K": K, "M": M, "crc": CRC24, "frames_per_step_per_gpu": frames_per_step,
+            "inputs": "CPU-resident float64 LLRs" if cpu else "fp32 LLR rows resident in HBM (larger than L2; no flush needed)",
+            "parallelism": f"frames sharded over {gpus} GPU(s), no data-path collective; int64 counter all-reduce per step"}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=1 << 22, help="frames per step per GPU (device-resident leg)")
+    ap.add_argument("--e2e-frames", type=int, default=1 << 21, help="frames per step per GPU (host-buffer leg)")
+    ap.add_argument("--cpu-sample", type=int, default=1_200_000, help="frames of the CPU baseline sample")
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from polar_code_b200.engine import PolarEngine, construct_info_set
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the polar_b200 engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    Ksteps = max(args.steps, 1)
+    B = args.frames
+
+    A = construct_info_set(N, K)
+    eng = PolarEngine(N, A, CRC24, device=local)
+    # synthetic input: Philox AWGN channel on the device (csrc/polar_sweep.cuh), one SNR point per slice
+    per = B // len(SNR_GRID)
+    parts, msgs = [], []
+    for i, s in enumerate(SNR_GRID):
+        nfr = per if i < len(SNR_GRID) - 1 else B - per * (len(SNR_GRID) - 1)
+        m, l = eng.channel(noise_var=noise_var(s), n_frames=nfr, frame_begin=rank * B + i * per, seed=2026, stream_id=i, k_payload=KP)
+        parts.append(l)
+        msgs.append(m)
+    llr = torch.cat(parts)
+    msg = torch.cat(msgs)
+    del parts, msgs
+    best_bits = torch.empty((B, K), dtype=torch.uint8, device=dev)
+    crc_ok = torch.empty((B,), dtype=torch.uint8, device=dev)
+    flags = torch.empty((B,), dtype=torch.int32, device=dev)
+    counters = torch.zeros(16, dtype=torch.int64, device=dev)
+
+    import ctypes as C
+    from polar_code_b200 import _lib as L
+    so = L.SclOut(best_bits=best_bits.data_ptr(), crc_ok=crc_ok.data_ptr(), flags=flags.data_ptr())
+    launches = {"n": 0}
+
+    def step():
+        L.check(eng.lib.pb200_scl_decode_batch(eng._h, C.c_void_p(llr.data_ptr()), B, N, None, M, C.byref(so),
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        launches["n"] += 1
+        if world > 1:
+            # per-step error counters reduced over NVLink; frames themselves never move
+            counters[0] = B
+            counters[1] = B - crc_ok.sum()
+            dist.all_reduce(counters)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(W):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches["n"] = 0
+    ms = timed(step, Ksteps)
+    n_launch = launches["n"]
+    clocks = sampler.stop() if rank == 0 else {}
+    value = world * B * Ksteps / (ms * 1e-3)
+
+    # correctness of what was timed: decisions vs the transmitted words
+    fer = float((~(best_bits == msg).all(dim=1)).float().mean().item())
+    crc_fail = float(1.0 - crc_ok.float().mean().item())
+    tie_frac = float((flags & 1).ne(0).float().mean().item())
+
+    # ---- e2e: host buffers through the C-ABI (pinned), copies inside the timed region --------------------
+    Be = min(args.e2e_frames, B)
+    h_llr = torch.empty((Be, N), dtype=torch.float32, pin_memory=True)
+    h_llr.copy_(llr[:Be])
+    h_bits = torch.empty((Be, K), dtype=torch.uint8, pin_memory=True)
+    h_ok = torch.empty((Be,), dtype=torch.uint8, pin_memory=True)
+    h_fl = torch.empty((Be,), dtype=torch.int32, pin_memory=True)
+
+    def e2e_step():
+        eng.scl_decode_host(h_llr, M, h_bits, h_ok, h_fl)
+
+    for _ in range(W):
+        e2e_step()
+    # pb200_scl_decode_host is synchronous and runs on the library's own copy/compute streams, so the region is
+    # timed on the host clock between two full device synchronisations (events on torch's stream would not see it)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ksteps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * Be * Ksteps / (e2e_ms * 1e-3)
+    assert torch.equal(h_bits.to(dev), best_bits[:Be]), "host-buffer path and device path disagree"
+
+    # ---- roofline -------------------------------------------------------------------------------------
+    pk = peaks()
+    ms_kernel = ms / Ksteps            # one decode_kernel launch per step, timed with CUDA events on its stream
+    ach_gbs = HBM_BYTES_PER_FRAME * B / (ms_kernel * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / pk["hbm_gbs"],
+                "traffic": None, "peak_source": pk["source"],
+                "note": "decode_kernel<4,7> is issue/shared-memory bound, not HBM bound (SURVEY 8(d)); see roofline_issue"}
+    lane_ops = ELEM_OPS[M] * B / (ms_kernel * 1e-3)
+    sm_clock = (clocks.get("sm_mhz") or pk["sm_max_mhz"]) * 1e6
+    props = torch.cuda.get_device_properties(dev)
+    peak_max = props.multi_processor_count * 128 * pk["sm_max_mhz"] * 1e6
+    roofline_issue = {"bound": "issue", "achieved": lane_ops, "unit": "element-ops/s (W_fg + W_pm = %d per frame)" % ELEM_OPS[M],
+                      "peak": peak_max, "frac": lane_ops / peak_max,
+                      "peak_at_measured_clock": props.multi_processor_count * 128 * sm_clock,
+                      "frac_at_measured_clock": lane_ops / (props.multi_processor_count * 128 * sm_clock)}
+
+    extras = {}
+    if not args.no_extras and rank == 0:
+        extras = extra_legs(eng, llr, msg, dev, B)
+
+    cb = cpu_baseline(args.cpu_sample) if (rank == 0 and world == 1) else None
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": Ksteps, "warmup": W,
+            "ms_per_step": ms / Ksteps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(B, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": Be * N * 4, "d2h_bytes_per_step": Be * (K + 1 + 4),
+                    "frames_per_step_per_gpu": Be, "ms_per_step": e2e_ms / Ksteps,
+                    "call": "pb200_scl_decode_host (pinned host LLRs -> best_bits, crc_ok, flags on the host)"},
+            "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "roofline_issue": roofline_issue,
+            "kernel": eng.kernel_info(M),
+            "check": {"fer_vs_sent": fer, "crc_fail_rate": crc_fail, "near_tie_flag_rate": tie_frac},
+        }
+        if cb:
+            line["cpu_baseline"] = cb
+        if extras:
+            line["extras"] = extras
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extra_legs(eng, llr, msg, dev, B) -> dict:
+    """Other BASELINE configs, timed the same way on rank 0 (informational; not the headline)."""
+    import torch
+    out = {}
+
+    def time_it(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    Bx = min(B, 1 << 21)
+    x = llr[:Bx]
+    for m in (1, 8):
+        ms = time_it(lambda: eng.scl_decode(x, m, want=("best_bits", "crc_ok", "flags")))
+        out[f"scl_M{m}_frames_per_s"] = Bx / (ms * 1e-3)
+    ms = time_it(lambda: eng.sc_decode(x))
+    out["sc_frames_per_s"] = Bx / (ms * 1e-3)
+    # fused Monte-Carlo sweep (Philox channel + SCL M=4 + counters), 5.0 dB
+    counters = torch.zeros(16, dtype=torch.int64, device=dev)
+    ms = time_it(lambda: eng.sweep(counters, M=M, noise_var=noise_var(5.0), n_frames=Bx, seed=1, stream_id=2, k_payload=KP))
+    out["fused_sweep_M4_frames_per_s"] = Bx / (ms * 1e-3)
+    # DL-SCL M=4, 8 retries, |L0| ranking (beta=None), 4.0 dB and 5.0 dB
+    for snr in (4.0, 5.0):
+        counters.zero_()
+        ms = time_it(lambda: eng.sweep(counters, M=M, noise_var=noise_var(snr), n_frames=Bx, seed=1, stream_id=3, k_payload=KP, retries=8))
+        out[f"fused_dlscl_M4_r8_{snr}dB_frames_per_s"] = Bx / (ms * 1e-3)
+    return out
+
+
+if __name__ == "__main__":
+    main()
