@@ -33,7 +33,7 @@ _f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 
 
 class _SclInfo(C.Structure):
-    _fields_ = [("n_cand", C.c_int), ("best_idx", C.c_int), ("min_rel_gap", C.c_double)]
+    _fields_ = [("n_cand", C.c_int), ("best_idx", C.c_int), ("min_rel_gap", C.c_double), ("min_rel_gap_prune", C.c_double)]
 
 
 class _DlInfo(C.Structure):

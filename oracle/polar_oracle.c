@@ -350,6 +350,7 @@ typedef struct {
     int n_cand;
     int best_idx;
     double min_rel_gap; /* smallest relative gap between competing metrics at any sort */
+    double min_rel_gap_prune; /* same, only at information-bit sorts and the final order */
 } scl_info;
 
 /*
@@ -374,7 +375,7 @@ int po_scl_decode(const double *llr, int N, const int32_t *info_set, int K, int 
     int np = 1, rc = PO_OK;
     paths[0] = path_new(N, n); /* :135 */
     for (int i = 0; i < N; i++) paths[0]->llr[i] = llr[i];
-    double min_gap = INFINITY;
+    double min_gap = INFINITY, min_gap_prune = INFINITY;
     int info_index = 0;
 
     for (int phase = 0; phase < N && rc == PO_OK; phase++) { /* :136 */
@@ -423,6 +424,7 @@ int po_scl_decode(const double *llr, int N, const int32_t *info_set, int K, int 
             double den = fabs(b) > fabs(a) ? fabs(b) : fabs(a);
             double gap = den > 0 ? (b - a) / den : 0.0;
             if (gap < min_gap) min_gap = gap;
+            if ((!frozen || phase == N - 1) && gap < min_gap_prune) min_gap_prune = gap;
         }
         np = nn < M ? nn : M; /* :174 */
         for (int i = 0; i < nn; i++) {
@@ -450,6 +452,7 @@ int po_scl_decode(const double *llr, int N, const int32_t *info_set, int K, int 
         info->n_cand = np;
         info->best_idx = best;
         info->min_rel_gap = min_gap;
+        info->min_rel_gap_prune = min_gap_prune;
     }
     for (int i = 0; i < np; i++) free(paths[i]);
     free(paths); free(next);
@@ -707,7 +710,7 @@ static void scl_one(void *v, int b) {
     if (r != PO_OK) { c->rc = r; return; }
     c->n_cand[b] = si.n_cand;
     c->best_idx[b] = si.best_idx;
-    c->min_gap[b] = si.min_rel_gap;
+    c->min_gap[b] = si.min_rel_gap_prune;
 }
 
 /* cand[B,M,K] metrics[B,M] info_llrs[B,M,K]|NULL n_cand[B] best_idx[B] min_gap[B]; force[B,K]|NULL */

@@ -15,6 +15,7 @@
 #include "../../include/polar_b200.h"
 #include "polar_kernels.cuh"
 #include "polar_sweep.cuh"
+#include "polar_launch.h"
 
 using namespace pb;
 
@@ -286,17 +287,8 @@ extern "C" int pb200_set_rate_matching(pb200_engine* e, int E) {
 // ---------------------------------------------------------------------------------------------------
 // Kernel selection
 // ---------------------------------------------------------------------------------------------------
-typedef void (*decode_fn)(const Code, const Tables, const DecodeArgs);
-
-template <int LOGMAX>
-static decode_fn pick_decode(int MP, bool forced, bool metric) {
-    if (!metric) return forced ? decode_kernel<1, LOGMAX, true, false> : decode_kernel<1, LOGMAX, false, false>;
-    switch (MP) {
-        case 1: return forced ? decode_kernel<1, LOGMAX, true, true> : decode_kernel<1, LOGMAX, false, true>;
-        case 2: return forced ? decode_kernel<2, LOGMAX, true, true> : decode_kernel<2, LOGMAX, false, true>;
-        case 4: return forced ? decode_kernel<4, LOGMAX, true, true> : decode_kernel<4, LOGMAX, false, true>;
-        default: return forced ? decode_kernel<8, LOGMAX, true, true> : decode_kernel<8, LOGMAX, false, true>;
-    }
+static const void* pick_decode(int n, int MP, bool forced, bool metric) {
+    return n <= 7 ? pb_decode_kernel_7(MP, forced, metric) : pb_decode_kernel_9(MP, forced, metric);
 }
 
 static int round_mp(int M) { return M <= 1 ? 1 : M <= 2 ? 2 : M <= 4 ? 4 : 8; }
@@ -337,9 +329,9 @@ static int choose_cfg(pb200_engine* e, const void* fn, int MP, int key_kind, siz
 static int launch_decode(pb200_engine* e, int M, bool metric, const DecodeArgs& a, cudaStream_t st) {
     const int MP = metric ? round_mp(M) : 1;
     const bool forced = a.force != nullptr;
-    decode_fn fn = e->code.n <= 7 ? pick_decode<7>(MP, forced, metric) : pick_decode<9>(MP, forced, metric);
+    const void* fn = pick_decode(e->code.n, MP, forced, metric);
     KernelCfg kc;
-    int rc = choose_cfg(e, (const void*)fn, MP, (forced ? 1 : 0) | (metric ? 2 : 0), warp_bytes(MP, e->code.N, 0), &kc);
+    int rc = choose_cfg(e, fn, MP, (forced ? 1 : 0) | (metric ? 2 : 0), warp_bytes(MP, e->code.N, 0), &kc);
     if (rc) return rc;
     Code code = e->code;
     code.M = metric ? M : 1;
@@ -347,8 +339,9 @@ static int launch_decode(pb200_engine* e, int M, bool metric, const DecodeArgs& 
     const int64_t groups = (a.B + fpw - 1) / fpw;
     const int64_t want = (groups + kc.wpc - 1) / kc.wpc;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)e->sms * kc.ctas_per_sm));
-    fn<<<grid, kc.wpc * 32, kc.smem, st>>>(code, e->tb, a);
-    CUDA_TRY(cudaGetLastError());
+    DecodeArgs aa = a;
+    void* args[3] = {(void*)&code, (void*)&e->tb, (void*)&aa};
+    CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(kc.wpc * 32), args, kc.smem, st));
     return PB200_OK;
 }
 
@@ -368,9 +361,9 @@ extern "C" int pb200_kernel_info(pb200_engine* e, int M, int* wpc, int* ctas, in
     if (M <= 0 || M > PB200_MAX_M) return fail(PB200_EINVAL, "bad M");
     CUDA_TRY(cudaSetDevice(e->device));
     const int MP = round_mp(M);
-    decode_fn fn = e->code.n <= 7 ? pick_decode<7>(MP, false, true) : pick_decode<9>(MP, false, true);
+    const void* fn = pick_decode(e->code.n, MP, false, true);
     KernelCfg kc;
-    int rc = choose_cfg(e, (const void*)fn, MP, 2, warp_bytes(MP, e->code.N, 0), &kc);
+    int rc = choose_cfg(e, fn, MP, 2, warp_bytes(MP, e->code.N, 0), &kc);
     if (rc) return rc;
     if (wpc) *wpc = kc.wpc;
     if (ctas) *ctas = kc.ctas_per_sm;

@@ -1,18 +1,6 @@
 // polar_abi_sweep.inl -- host side of the Monte-Carlo sweep, DL-SCL rounds, channel generator, NR encoder.
 // Included at the end of polar_abi.cu.
 
-typedef void (*sweep_fn)(const Code, const Tables, const SweepArgs);
-
-template <int LOGMAX>
-static sweep_fn pick_sweep(int MP, bool round) {
-    switch (MP) {
-        case 1: return round ? dl_round_kernel<1, LOGMAX> : sweep_kernel<1, LOGMAX>;
-        case 2: return round ? dl_round_kernel<2, LOGMAX> : sweep_kernel<2, LOGMAX>;
-        case 4: return round ? dl_round_kernel<4, LOGMAX> : sweep_kernel<4, LOGMAX>;
-        default: return round ? dl_round_kernel<8, LOGMAX> : sweep_kernel<8, LOGMAX>;
-    }
-}
-
 int sweep_build_tables(pb200_engine* e) {
     const int N = e->code.N;
     std::vector<int16_t> id(N);
@@ -81,10 +69,10 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
     const bool big = e->code.n > 7;
     Code code = e->code;
     code.M = M;
-    sweep_fn base = big ? pick_sweep<9>(MP, false) : pick_sweep<7>(MP, false);
-    sweep_fn round = big ? pick_sweep<9>(MP, true) : pick_sweep<7>(MP, true);
+    const void* base = big ? pb_sweep_kernel_9(MP, false) : pb_sweep_kernel_7(MP, false);
+    const void* round = big ? pb_sweep_kernel_9(MP, true) : pb_sweep_kernel_7(MP, true);
     KernelCfg kb, kr;
-    int rc = choose_cfg(e, (const void*)base, MP, 4, warp_bytes(MP, code.N, 0), &kb);
+    int rc = choose_cfg(e, base, MP, 4, warp_bytes(MP, code.N, 0), &kb);
     if (rc) return rc;
     const int fpw = 32 / MP;
     const long long piece_max = 1ll << 22;
@@ -125,10 +113,12 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
         const long long groups = (nf + fpw - 1) / fpw;
         const long long want = (groups + kb.wpc - 1) / kb.wpc;
         const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)e->sms * kb.ctas_per_sm));
-        base<<<grid, kb.wpc * 32, kb.smem, st>>>(code, e->tb, p);
-        CUDA_TRY(cudaGetLastError());
+        {
+            void* args[3] = {(void*)&code, (void*)&e->tb, (void*)&p};
+            CUDA_TRY(cudaLaunchKernel(base, dim3(grid), dim3(kb.wpc * 32), args, kb.smem, st));
+        }
         if (a.retries > 0) {
-            rc = choose_cfg(e, (const void*)round, MP, 5, warp_bytes(MP, code.N, code.K), &kr);
+            rc = choose_cfg(e, round, MP, 5, warp_bytes(MP, code.N, code.K), &kr);
             if (rc) return rc;
             const long long rgroups = (nf + fpw - 1) / fpw;
             const long long rwant = (rgroups + kr.wpc - 1) / kr.wpc;
@@ -139,8 +129,8 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
                 q.q_in_count = e->d_q_counts + r;
                 q.q_out = e->d_q[(r + 1) & 1];
                 q.q_out_count = e->d_q_counts + r + 1;
-                round<<<rgrid, kr.wpc * 32, kr.smem, st>>>(code, e->tb, q);
-                CUDA_TRY(cudaGetLastError());
+                void* args[3] = {(void*)&code, (void*)&e->tb, (void*)&q};
+                CUDA_TRY(cudaLaunchKernel(round, dim3(rgrid), dim3(kr.wpc * 32), args, kr.smem, st));
             }
         }
     }
@@ -208,12 +198,12 @@ extern "C" int pb200_channel_batch(pb200_engine* e, const pb200_sweep_cfg* c, ui
     const int wpc = 4;
     const long long groups = (c->n_frames + 7) / 8;
     const int grid = (int)std::max<long long>(1, std::min<long long>((groups + wpc - 1) / wpc, (long long)e->sms * 8));
-    if (e->code.n <= 7) {
-        CUDA_TRY(cudaFuncSetAttribute(channel_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wb * wpc)));
-        channel_kernel<7><<<grid, wpc * 32, wb * wpc, (cudaStream_t)stream>>>(e->code, e->tb, a, d_msg, d_llr);
-    } else {
-        CUDA_TRY(cudaFuncSetAttribute(channel_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wb * wpc)));
-        channel_kernel<9><<<grid, wpc * 32, wb * wpc, (cudaStream_t)stream>>>(e->code, e->tb, a, d_msg, d_llr);
+    {
+        const void* fn = pb_channel_kernel(e->code.n);
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wb * wpc)));
+        Code code = e->code;
+        void* args[5] = {(void*)&code, (void*)&e->tb, (void*)&a, (void*)&d_msg, (void*)&d_llr};
+        CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(wpc * 32), args, wb * wpc, (cudaStream_t)stream));
     }
     CUDA_TRY(cudaGetLastError());
     return PB200_OK;

@@ -132,26 +132,14 @@ struct ListDecoder {
                     bit = pick1 ? 1u : 0u;
                 } else {
                     const unsigned long long dead = ~0ull;
-                    const unsigned long long k0 = a0 ? (((unsigned long long)__double_as_longlong(m0) & ~15ull) | (2u * p.r)) : dead;
                     if (!is_info) {
-                        // frozen phase: one child per path, re-rank the list (scl.py:149-153,173)
-                        wm.xchg[lane * 2] = k0;
-                        __syncwarp();
-                        uint32_t rank0 = 0, cnt0 = 0;
-                        const uint32_t h0 = (uint32_t)(k0 >> 32);
-#pragma unroll
-                        for (int j = 0; j < MP; ++j) {
-                            const unsigned long long o = wm.xchg[(gbase + j) * 2];
-                            rank0 += (o < k0);
-                            cnt0 += ((uint32_t)((uint32_t)(o >> 32) - h0 + 2u) <= 4u);
-                        }
-                        if (a0) {
-                            if (cnt0 >= 2) tie = 1;
-                            p.m = m0;
-                            p.r = rank0;
-                        }
+                        // frozen phase (scl.py:149-153): one child per path.  The reference re-sorts here too (:173),
+                        // but a rank is only ever used as the tie-break between EXACTLY equal metrics, so the
+                        // re-ranking is deferred to the next prune / the final ordering (rank_final below).
+                        if (a0) p.m = m0;
                         bit = 0;
                     } else {
+                        const unsigned long long k0 = a0 ? (((unsigned long long)__double_as_longlong(m0) & ~15ull) | (2u * p.r)) : dead;
                         const unsigned long long k1 = a1 ? (((unsigned long long)__double_as_longlong(m1) & ~15ull) | (2u * p.r + 1u)) : dead;
                         reinterpret_cast<ulonglong2*>(wm.xchg)[lane] = make_ulonglong2(k0, k1);
                         __syncwarp();
@@ -200,6 +188,22 @@ struct ListDecoder {
             }
             if (p.alive) set_bit(code, p, phi, bit);
             if constexpr (MP > 1) __syncwarp();
+        }
+        // final list order = metric order (scl.py:173-174,183-188), ties by the last computed rank
+        if constexpr (MP > 1) {
+            const unsigned long long kf = p.alive ? (((unsigned long long)__double_as_longlong(p.m) & ~15ull) | p.r) : ~0ull;
+            wm.xchg[lane] = kf;
+            __syncwarp();
+            uint32_t rank = 0, cnt = 0;
+            const uint32_t hf = (uint32_t)(kf >> 32);
+#pragma unroll
+            for (int j = 0; j < MP; ++j) {
+                const unsigned long long o = wm.xchg[gbase + j];
+                rank += (o < kf);
+                cnt += ((uint32_t)((uint32_t)(o >> 32) - hf + 2u) <= 4u);
+            }
+            if (p.alive) { p.r = rank; if (cnt >= 2) tie = 1; }
+            __syncwarp();
         }
         if (tie) flags |= PB_FLAG_NEAR_TIE;
     }

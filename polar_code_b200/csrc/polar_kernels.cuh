@@ -35,13 +35,30 @@ __device__ __forceinline__ void load_channel(const Code& code, const Tables& tb,
                                              int in_len, int64_t frame0, int64_t B, int lane) {
     constexpr int FPW = 32 / MP;
     const int N = code.N, n = code.n;
-    for (int e = lane; e < FPW * N; e += 32) {
-        const int f = e >> n, i = e & (N - 1);
-        const int64_t frame = frame0 + f;
-        float v = 0.f;
-        if (frame < B) {
-            if (tb.E == 0) v = llr[frame * (int64_t)in_len + i];
-            else {
+    if (tb.E == 0) {
+        // plain rows: FPW*N consecutive floats; issue the loads in batches of 8 so they overlap in flight
+        const int total = FPW * N;
+        const float* base = llr + frame0 * (int64_t)in_len;
+        const int64_t avail = (B - frame0) * (int64_t)N;     // floats that exist behind `base`
+        for (int e0 = 0; e0 < total; e0 += 32 * 8) {
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int e = e0 + k * 32 + lane;
+                v[k] = (e < total && e < avail) ? __ldcs(base + e) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int e = e0 + k * 32 + lane;
+                if (e < total) wm.chan[(e >> n) * (N + 1) + (e & (N - 1))] = v[k];
+            }
+        }
+    } else {
+        for (int e = lane; e < FPW * N; e += 32) {
+            const int f = e >> n, i = e & (N - 1);
+            const int64_t frame = frame0 + f;
+            float v = 0.f;
+            if (frame < B) {
                 const int p = tb.rm_src[i];
                 if (p >= 0) {
                     float acc = 0.f;
@@ -50,8 +67,8 @@ __device__ __forceinline__ void load_channel(const Code& code, const Tables& tb,
                     v = cnt ? acc / (float)cnt : -1.0f;
                 }
             }
+            wm.chan[f * (N + 1) + i] = v;
         }
-        wm.chan[f * (N + 1) + i] = v;
     }
     __syncwarp();
 }
@@ -187,7 +204,7 @@ __global__ void decode_kernel(const Code code, const Tables tb, const DecodeArgs
 // ---------------------------------------------------------------------------
 // Encoder (polar.py:106-119): one thread per frame, msg[B,K] u8 -> code[B,N] u8.
 // ---------------------------------------------------------------------------
-__global__ void encode_kernel(const Code code, const Tables tb, const uint8_t* __restrict__ msg, uint8_t* __restrict__ out, int64_t B) {
+static __global__ void encode_kernel(const Code code, const Tables tb, const uint8_t* __restrict__ msg, uint8_t* __restrict__ out, int64_t B) {
     const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= B) return;
     uint32_t u[kMaxWords];
@@ -212,7 +229,7 @@ __global__ void encode_kernel(const Code code, const Tables tb, const uint8_t* _
 // CRC (crc.py:19-56): bit-serial long division, MSB first, zero init, one thread per frame.
 // poly has degree `deg` (<= 63) with the leading 1 at bit `deg`.
 // ---------------------------------------------------------------------------
-__global__ void crc_kernel(unsigned long long poly, int deg, const uint8_t* __restrict__ msg, int L, int64_t B,
+static __global__ void crc_kernel(unsigned long long poly, int deg, const uint8_t* __restrict__ msg, int L, int64_t B,
                            uint8_t* __restrict__ out_attach, uint8_t* __restrict__ out_ok) {
     const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= B) return;

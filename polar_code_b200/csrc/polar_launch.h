@@ -1,0 +1,8 @@
+// polar_launch.h -- kernel lookup across translation units.  Each k_*.cu instantiates one family of kernels and
+// returns host-side function pointers; polar_abi.cu launches them with cudaLaunchKernel.
+#pragma once
+const void* pb_decode_kernel_7(int MP, bool forced, bool metric);
+const void* pb_decode_kernel_9(int MP, bool forced, bool metric);
+const void* pb_sweep_kernel_7(int MP, bool round);
+const void* pb_sweep_kernel_9(int MP, bool round);
+const void* pb_channel_kernel(int logmax);

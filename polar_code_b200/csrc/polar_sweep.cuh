@@ -613,7 +613,7 @@ __global__ void channel_kernel(const Code code, const Tables tb, const SweepArgs
 }
 
 // choose_flip_index (flip.py:13-27): one block per row, argmin(abs_l0 @ beta) / argmin(abs_l0), first minimum.
-__global__ void flip_index_kernel(const float* __restrict__ abs_l0, const float* __restrict__ beta, int32_t* __restrict__ out, int K) {
+static __global__ void flip_index_kernel(const float* __restrict__ abs_l0, const float* __restrict__ beta, int32_t* __restrict__ out, int K) {
     extern __shared__ double qs[];
     const long long row = blockIdx.x;
     for (int j = threadIdx.x; j < K; j += blockDim.x) {
@@ -631,7 +631,7 @@ __global__ void flip_index_kernel(const float* __restrict__ abs_l0, const float*
 }
 
 // encode_rate_matched (scl_nr.py:23-35): payload[B,Kp] -> CRC -> encode -> interleave -> rate-match; one thread per frame.
-__global__ void nr_encode_kernel(const Code code, const Tables tb, const ChanCfg cc, const uint8_t* __restrict__ payload, int8_t* __restrict__ tx,
+static __global__ void nr_encode_kernel(const Code code, const Tables tb, const ChanCfg cc, const uint8_t* __restrict__ payload, int8_t* __restrict__ tx,
                                  long long B, int E) {
     const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= B) return;
