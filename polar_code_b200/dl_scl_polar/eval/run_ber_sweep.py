@@ -155,8 +155,11 @@ def plot_rows(rows: List[Dict[str, float]], path: Path) -> None:
 
 def main(argv: Optional[Iterable[str]] = None) -> None:
     args = parse_args(argv)
+    started_here = mc.world()[1] == 1
     rows = run(args)
-    if mc.world()[0] != 0:
+    is_writer = mc.world()[0] == 0
+    mc.shutdown_distributed(started_here)
+    if not is_writer:
         return
     out_path = Path(args.out)
     out_path.parent.mkdir(parents=True, exist_ok=True)

@@ -100,10 +100,12 @@ def write_outputs(args: argparse.Namespace, rows: List[Dict[str, float]]) -> Non
 
 
 def run_sweep(args: argparse.Namespace) -> None:
+    started_here = mc.world()[1] == 1
     mc.maybe_init_distributed()
     rows = sweep_rows(args)
     if mc.world()[0] == 0:
         write_outputs(args, rows)
+    mc.shutdown_distributed(started_here)
 
 
 _FLAGS = [

@@ -43,6 +43,12 @@ def maybe_init_distributed() -> Tuple[int, int]:
     return world()
 
 
+def shutdown_distributed(started_here: bool) -> None:
+    """Leave the process group again if maybe_init_distributed() created it."""
+    if started_here and dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
+
+
 def shard_range(n_frames: int, rank: int, world_size: int) -> Tuple[int, int]:
     """Contiguous [begin, begin+count) slice of range(n_frames) owned by `rank` (sizes differ by at most one)."""
     base, rem = divmod(int(n_frames), int(world_size))
