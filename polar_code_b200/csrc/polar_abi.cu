@@ -128,6 +128,8 @@ struct pb200_engine {
     size_t q_bytes = 0;
     unsigned int* d_q_counts = nullptr;
     int q_counts_n = 0;
+    unsigned char* d_scratch = nullptr;   // per-warp global scratch of the decode kernels
+    size_t scratch_bytes = 0;
 };
 int sweep_build_tables(pb200_engine* e);
 
@@ -242,7 +244,7 @@ extern "C" void pb200_destroy(pb200_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaFree(e->d_info_pos); cudaFree(e->d_crc_tab); cudaFree(e->d_rm_src); cudaFree(e->d_tx_src); cudaFree(e->d_enc_tab);
-    cudaFree(e->d_rm_dst); cudaFree(e->d_q[0]); cudaFree(e->d_q[1]); cudaFree(e->d_q_counts);
+    cudaFree(e->d_scratch); cudaFree(e->d_rm_dst); cudaFree(e->d_q[0]); cudaFree(e->d_q[1]); cudaFree(e->d_q_counts);
     for (int i = 0; i < 3; ++i) {
         if (e->hs[i]) cudaStreamDestroy(e->hs[i]);
         cudaFree(e->d_stage_llr[i]); cudaFree(e->d_stage_bits[i]); cudaFree(e->d_stage_ok[i]); cudaFree(e->d_stage_flags[i]);
@@ -293,6 +295,27 @@ static const void* pick_decode(int n, int MP, bool forced, bool metric) {
 
 static int round_mp(int M) { return M <= 1 ? 1 : M <= 2 ? 2 : M <= 4 ? 4 : 8; }
 
+static size_t warp_gbytes(int MP, int N) {
+    switch (MP) {
+        case 1: return WarpMem<1>::gbytes(N);
+        case 2: return WarpMem<2>::gbytes(N);
+        case 4: return WarpMem<4>::gbytes(N);
+        default: return WarpMem<8>::gbytes(N);
+    }
+}
+
+// global scratch for `warps` resident warps (grows on demand; stays L2-resident across launches)
+static int ensure_scratch(pb200_engine* e, size_t warps, int MP) {
+    const size_t need = warps * warp_gbytes(MP, e->code.N) + 256;
+    if (e->scratch_bytes < need) {
+        cudaFree(e->d_scratch);
+        e->d_scratch = nullptr; e->scratch_bytes = 0;
+        CUDA_TRY(cudaMalloc((void**)&e->d_scratch, need));
+        e->scratch_bytes = need;
+    }
+    return PB200_OK;
+}
+
 static size_t warp_bytes(int MP, int N, int xk) {
     switch (MP) {
         case 1: return WarpMem<1>::bytes(N, xk);
@@ -339,7 +362,10 @@ static int launch_decode(pb200_engine* e, int M, bool metric, const DecodeArgs& 
     const int64_t groups = (a.B + fpw - 1) / fpw;
     const int64_t want = (groups + kc.wpc - 1) / kc.wpc;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)e->sms * kc.ctas_per_sm));
+    rc = ensure_scratch(e, (size_t)grid * kc.wpc, MP);
+    if (rc) return rc;
     DecodeArgs aa = a;
+    aa.gscratch = e->d_scratch;
     void* args[3] = {(void*)&code, (void*)&e->tb, (void*)&aa};
     CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(kc.wpc * 32), args, kc.smem, st));
     return PB200_OK;

@@ -66,26 +66,59 @@ __device__ __forceinline__ float softplus_tail(float L) { return log1pf(expf(-fa
 __device__ __forceinline__ bool info_bit(const Code& c, int phi) { return (c.info_mask[phi >> 5] >> (phi & 31)) & 1u; }
 
 // ---------------------------------------------------------------------------
-// Per-warp shared-memory view.
+// Per-warp memory view.
+//   shared : tree heights 1..HSPLIT-1 (lane-interleaved), rank-exchange area, DL-SCL |L0| rows
+//   global : tree heights HSPLIT..n-1 (same lane-interleaved layout: one 128 B line per warp access) and the
+//            staged channel row when the LLRs are generated / de-rate-matched on the fly.  The scratch of all
+//            resident warps (~16 KB each) stays L2-resident; moving the two big heights out of shared memory is
+//            what lifts occupancy from 11 to ~28 warps per SM for N = 128.
 // ---------------------------------------------------------------------------
+#ifndef PB_HSPLIT
+#define PB_HSPLIT 5
+#endif
+constexpr int kHSplit = PB_HSPLIT;
+
+__host__ __device__ inline int tree_rows_shared(int N) {
+    const int all = N >= 6 ? N - 2 : 4;                 // rows of heights 1..n-1 (at least 4 rows of scratch)
+    const int cap = (1 << kHSplit) - 2;
+    return all < cap ? all : cap;
+}
+__host__ __device__ inline int tree_rows_global(int N) {
+    const int all = N >= 6 ? N - 2 : 4;
+    const int cap = (1 << kHSplit) - 2;
+    return all > cap ? all - cap : 0;
+}
+
+constexpr int kXchgBytes = 32 * 16 + 32 * 2 * 4;   // candidate keys + rank-sorted high words
+
 template <int MP>
 struct WarpMem {
-    float* tree;          // [(2^n - 2)][32]   heights 1..n-1, lane-interleaved
-    float* chan;          // [FPW][N+1]        channel LLRs (height n), shared by the MP paths of a frame
-    unsigned long long* xchg;  // [32][2]      candidate keys for the rank exchange / small per-frame scratch
-    float* absl;          // [FPW][xk+1]       DL-SCL only: |L0| of the reference path (flip.py:102)
+    float* ts;            // shared tree base:  element (h,i), h <  HSPLIT, at ts[((2^h-2)+i)*32 + lane]
+    float* tg;            // global tree base (pre-offset): element (h,i), h >= HSPLIT, at tg[((2^h-2)+i)*32 + lane]
+    float* chan;          // [FPW][N+1] staged channel LLRs (global scratch); unused when rows are read in place
+    float* scr;           // >= 3*max(N/32,1) lane-interleaved rows of scratch for the encoder / bit stash
+    unsigned long long* xchg;  // [32][2] candidate keys for the rank exchange / small per-frame scratch (shared)
+    float* absl;          // [FPW][xk+1] DL-SCL only: |L0| of the reference path (flip.py:102) (shared)
     static constexpr int FPW = 32 / MP;
-    __host__ __device__ static size_t tree_bytes(int N) { return (size_t)(N >= 6 ? N - 2 : 4) * 32 * 4; }
-    __host__ __device__ static size_t chan_bytes(int N) { return ((size_t)FPW * (N + 1) * 4 + 15) & ~(size_t)15; }
-    __host__ __device__ static size_t bytes(int N, int xk = 0) {
+    __host__ __device__ static size_t tree_bytes(int N) { return (size_t)tree_rows_shared(N) * 32 * 4; }
+    __host__ __device__ static size_t bytes(int N, int xk = 0) {          // shared bytes per warp
         size_t x = xk ? (((size_t)FPW * (xk + 1) * 4 + 15) & ~(size_t)15) : 0;
-        return tree_bytes(N) + chan_bytes(N) + 32 * 16 + x;
+        return tree_bytes(N) + kXchgBytes + x;
     }
-    __device__ void carve(unsigned char* base, int N) {
-        tree = reinterpret_cast<float*>(base);
-        chan = reinterpret_cast<float*>(base + tree_bytes(N));
-        xchg = reinterpret_cast<unsigned long long*>(base + tree_bytes(N) + chan_bytes(N));
-        absl = reinterpret_cast<float*>(base + tree_bytes(N) + chan_bytes(N) + 32 * 16);
+    __host__ __device__ static size_t gbytes(int N) {                     // global scratch bytes per warp
+        size_t t = (size_t)tree_rows_global(N) * 32 * 4;
+        size_t ch = (((size_t)FPW * (N + 1) * 4) + 127) & ~(size_t)127;
+        return t + ch;
+    }
+    __device__ void carve(unsigned char* sbase, unsigned char* gbase, int N) {
+        ts = reinterpret_cast<float*>(sbase);
+        xchg = reinterpret_cast<unsigned long long*>(sbase + tree_bytes(N));
+        absl = reinterpret_cast<float*>(sbase + tree_bytes(N) + kXchgBytes);
+        float* g = reinterpret_cast<float*>(gbase);
+        tg = g - ((1 << kHSplit) - 2) * 32;
+        chan = g + (size_t)tree_rows_global(N) * 32;
+        const int need = 3 * (N >= 32 ? N / 32 : 1);
+        scr = (tree_rows_shared(N) >= need) ? ts : g;
     }
 };
 
@@ -192,65 +225,77 @@ struct Path {
 };
 
 // ---------------------------------------------------------------------------
-// LLR tree evaluation.
+// LLR tree evaluation.  Every routine stops at the height-1 pair (a, b): the two leaves of a phase pair are
+// f(a,b) and g(a,b,u_even) and never touch memory.
 // ---------------------------------------------------------------------------
 template <int MP, int LOGMAX>
 struct Tree {
     using PathT = Path<LOGMAX>;
     static constexpr int BW = PathT::BW;
 
-    // down from 2^H register values to the leaf; heights H-1..1 are stored in the own slot
+    template <int H> static __device__ __forceinline__ float* base(const WarpMem<MP>& wm) { return (H >= kHSplit) ? wm.tg : wm.ts; }
+
+    // 2^H register values (H >= 1) -> height-1 pair; heights H-1..2 are stored in the own slot
     template <int H>
-    static __device__ __forceinline__ float reg_chain(float (&v)[1 << H], float* own) {
-        if constexpr (H == 0) return v[0];
+    static __device__ __forceinline__ void reg_chain(float (&v)[1 << H], const WarpMem<MP>& wm, int lane, float& a, float& b) {
+        if constexpr (H == 1) { a = v[0]; b = v[1]; }
         else {
-            float w[(1 << H) / 2 > 0 ? (1 << H) / 2 : 1];
+            float w[(1 << H) / 2];
+            float* own = base<H - 1>(wm) + lane;
 #pragma unroll
             for (int i = 0; i < (1 << (H - 1)); ++i) {
                 w[i] = f_op(v[i], v[i + (1 << (H - 1))]);
-                if constexpr (H - 1 >= 1) own[(((1 << (H - 1)) - 2) + i) * 32] = w[i];
+                if constexpr (H - 1 >= 2) own[(((1 << (H - 1)) - 2) + i) * 32] = w[i];
             }
-            return reg_chain<H - 1>(w, own);
+            reg_chain<H - 1>(w, wm, lane, a, b);
         }
     }
 
-    // Produce height H from height H+1 stored at src[i*stride] (OP 0 = f, 1 = g with the left bits
-    // of height H), store it in the own slot, continue with f down to the leaf.  Returns the leaf LLR.
+    // Produce height H (>= 1) from height H+1 held at src[i*32] (tree, slot lane already folded into src) with
+    // OP 0 = f, 1 = g using the left bits of height H; store it in the own slot; continue with f down to the pair.
     template <int H, int OP>
-    static __device__ __forceinline__ float produce(const float* src, int stride, const uint32_t (&bw)[BW], float* own) {
+    static __device__ __forceinline__ void produce(const float* src, const uint32_t (&bw)[BW], const WarpMem<MP>& wm, int lane,
+                                                   float& a, float& b) {
         constexpr int S = 1 << H;
+        float* own = base<H>(wm) + lane;
         if constexpr (H <= 3) {
             float v[S];
 #pragma unroll
             for (int i = 0; i < S; ++i) {
-                float a = src[i * stride], b = src[(i + S) * stride];
-                v[i] = OP ? g_op(a, b, left_bit<H, BW>(bw, i)) : f_op(a, b);
-                if constexpr (H >= 1) own[((S - 2) + i) * 32] = v[i];
+                const float x = src[i * 32], y = src[(i + S) * 32];
+                v[i] = OP ? g_op(x, y, left_bit<H, BW>(bw, i)) : f_op(x, y);
+                if constexpr (H >= 2) own[((S - 2) + i) * 32] = v[i];
             }
-            return reg_chain<H>(v, own);
+            reg_chain<H>(v, wm, lane, a, b);
         } else {
             float* dst = own + (S - 2) * 32;
             if constexpr (OP == 0) {
-#pragma unroll 4
-                for (int i = 0; i < S; ++i) dst[i * 32] = f_op(src[i * stride], src[(i + S) * stride]);
+#pragma unroll 8
+                for (int i = 0; i < S; ++i) dst[i * 32] = f_op(src[i * 32], src[(i + S) * 32]);
             } else if constexpr (H == 4) {
                 const uint32_t bits = bw[0] >> 15;
-#pragma unroll 4
-                for (int i = 0; i < S; ++i) dst[i * 32] = g_op(src[i * stride], src[(i + S) * stride], (bits >> i) & 1u);
+#pragma unroll 8
+                for (int i = 0; i < S; ++i) dst[i * 32] = g_op(src[i * 32], src[(i + S) * 32], (bits >> i) & 1u);
             } else {
                 constexpr int W0 = (H == 5) ? 1 : (H == 6) ? 2 : (H == 7) ? 4 : 8;  // first word of height H
 #pragma unroll
                 for (int w = 0; w < S / 32; ++w) {
                     const uint32_t bits = bw[(W0 + w) < BW ? (W0 + w) : 0];
-#pragma unroll 4
+#pragma unroll 8
                     for (int j = 0; j < 32; ++j) {
                         const int i = w * 32 + j;
-                        dst[i * 32] = g_op(src[i * stride], src[(i + S) * stride], (bits >> j) & 1u);
+                        dst[i * 32] = g_op(src[i * 32], src[(i + S) * 32], (bits >> j) & 1u);
                     }
                 }
             }
-            return produce<H - 1, 0>(dst, 32, bw, own);
+            produce<H - 1, 0>(dst, bw, wm, lane, a, b);
         }
+    }
+
+    // f-chain from the own slot's height H (>= 2) down to the pair
+    template <int H>
+    static __device__ __forceinline__ void chain_from(const uint32_t (&bw)[BW], const WarpMem<MP>& wm, int lane, float& a, float& b) {
+        produce<H - 1, 0>(base<H>(wm) + lane + (((1 << H) - 2) * 32), bw, wm, lane, a, b);
     }
 };
 

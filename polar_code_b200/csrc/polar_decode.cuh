@@ -14,49 +14,77 @@ struct ListDecoder {
     static constexpr int FPW = 32 / MP;
     static constexpr uint32_t GM = (MP >= 32) ? 0xffffffffu : ((1u << MP) - 1u);
 
-    // leaf LLR of `phi` for this lane's path (lazy form of scl.py:64-82)
-    static __device__ __forceinline__ float leaf_llr(const Code& code, const WarpMem<MP>& wm, PathT& p, int phi,
-                                                     int lane) {
+    // word w of the left-child bit buffer of height h (runtime h; warp-uniform selects)
+    static __device__ __forceinline__ uint32_t height_word(const uint32_t (&bw)[BW], int h, int w) {
+        if (h < 5) return bw[0] >> ((1 << h) - 1);
+        if (h == 5) return bw[1];
+        uint32_t r = 0;
+        const int first = (h == 6) ? 2 : (h == 7) ? 4 : 8;
+#pragma unroll
+        for (int k = 2; k < BW; ++k) if (k == first + w) r = bw[k];
+        return r;
+    }
+
+    // height n-1 from the channel row: f at phi = 0, g (left bits of height n-1) at phi = N/2.  Runtime-sized loop;
+    // `chanf` may point into the caller's LLR buffer (global) or into the staged row.
+    static __device__ __forceinline__ void top_level(const Code& code, const WarpMem<MP>& wm, const PathT& p, bool is_g, int lane,
+                                                     const float* chanf, float& a, float& b) {
+        const int half = code.N >> 1, h = code.n - 1;
+        if (half == 2) {  // N = 4: height 1 is the pair itself
+            const float v0 = is_g ? g_op(chanf[0], chanf[2], (p.bw[0] >> 1) & 1u) : f_op(chanf[0], chanf[2]);
+            const float v1 = is_g ? g_op(chanf[1], chanf[3], (p.bw[0] >> 2) & 1u) : f_op(chanf[1], chanf[3]);
+            a = v0; b = v1;
+            return;
+        }
+        float* dst = ((h >= kHSplit) ? wm.tg : wm.ts) + lane + (half - 2) * 32;
+        const int nw = half >= 32 ? half / 32 : 1, per = half >= 32 ? 32 : half;
+        for (int w = 0; w < nw; ++w) {
+            const float* x = chanf + w * 32;
+            float* d = dst + w * 32 * 32;
+            if (!is_g) {
+#pragma unroll 8
+                for (int j = 0; j < per; ++j) d[j * 32] = f_op(x[j], x[j + half]);
+            } else {
+                const uint32_t bits = height_word(p.bw, h, w);
+#pragma unroll 8
+                for (int j = 0; j < per; ++j) d[j * 32] = g_op(x[j], x[j + half], (bits >> j) & 1u);
+            }
+        }
+    }
+
+    // height-1 pair (a, b) of this lane's path for the EVEN phase `phi` (lazy form of scl.py:64-82)
+    static __device__ __forceinline__ void pair_llr(const Code& code, const WarpMem<MP>& wm, PathT& p, int phi, int lane,
+                                                    const float* chanf, float& a, float& b) {
         const int n = code.n;
         const int slot = lane & (MP - 1), gbase = lane & ~(MP - 1);
-        float* own = wm.tree + lane;
-        const float* chanf = wm.chan + (lane / MP) * (code.N + 1);
-        float leaf = 0.f;
-        int c;
-        if (phi == 0) {
-            c = n - 1;
-            switch (n) {
-#define PB_CASE(NN) case NN: if constexpr (NN <= LOGMAX) leaf = TreeT::template produce<NN - 1, 0>(chanf, 1, p.bw, own); break;
-                PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7) PB_CASE(8) PB_CASE(9)
+        if (n == 1) { a = chanf[0]; b = chanf[1]; return; }      // N = 2: the channel row is the pair
+        const int c = (phi == 0) ? n - 1 : __ffs(phi) - 1;       // first height produced (>= 1)
+        if (c == n - 1) {
+            top_level(code, wm, p, phi != 0, lane, chanf, a, b);
+            switch (c) {
+#define PB_CASE(HH) case HH: if constexpr (HH < LOGMAX) TreeT::template chain_from<HH>(p.bw, wm, lane, a, b); break;
+                PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7) PB_CASE(8)
 #undef PB_CASE
-                default: break;
+                default: break;   // c == 1: top_level returned the pair
             }
         } else {
-            c = __ffs(phi) - 1;
-            const float* src;
-            int stride;
-            if (c + 1 == n) { src = chanf; stride = 1; }
-            else {
-                const uint32_t q = (p.P >> (4 * c)) & 0xfu;            // slot holding height c+1 (field c)
-                src = wm.tree + (((2 << c) - 2) * 32) + gbase + q;
-                stride = 32;
-            }
+            const uint32_t q = (p.P >> (4 * c)) & 0xfu;          // slot holding height c+1 (field c)
+            const float* src = ((c + 1 >= kHSplit) ? wm.tg : wm.ts) + (((2 << c) - 2) * 32) + gbase + q;
             switch (c) {
-#define PB_CASE(CC) case CC: if constexpr (CC < LOGMAX) leaf = TreeT::template produce<CC, 1>(src, stride, p.bw, own); break;
-                PB_CASE(0) PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7) PB_CASE(8)
+#define PB_CASE(CC) case CC: if constexpr (CC + 1 < LOGMAX) TreeT::template produce<CC, 1>(src, p.bw, wm, lane, a, b); break;
+                PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7)
 #undef PB_CASE
                 default: break;
             }
         }
-        // heights 1..c now live in the own slot
+        // heights 2..c now live in the own slot
         const uint32_t mask = (c >= 8) ? 0xffffffffu : ((1u << (4 * c)) - 1u);
         p.P = (p.P & ~mask) | ((slot * 0x11111111u) & mask);
-        return leaf;
     }
 
-    // scl.py:84-99 in packed form
-    static __device__ __forceinline__ void set_bit(const Code& code, PathT& p, int phi, uint32_t bit) {
-        const int t = __ffs(~phi) - 1;  // trailing ones of phi
+    // scl.py:84-99 in packed form, for an ODD phase (at least one trailing one)
+    static __device__ __forceinline__ void set_bit_odd(const Code& code, PathT& p, int phi, uint32_t bit) {
+        const int t = __ffs(~phi) - 1;  // trailing ones of phi, >= 1
         switch (t) {
 #define PB_CASE(TT)                                                                     \
     case TT:                                                                            \
@@ -69,7 +97,7 @@ struct ListDecoder {
             } else if constexpr (TT < LOGMAX) store_height<TT, BW, CW>(p.bw, cw);       \
         }                                                                               \
         break;
-            PB_CASE(0) PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7) PB_CASE(8) PB_CASE(9)
+            PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7) PB_CASE(8) PB_CASE(9)
 #undef PB_CASE
             default: break;
         }
@@ -86,15 +114,19 @@ struct ListDecoder {
         p.alive = frame_valid && ((lane & (MP - 1)) == 0);   // scl.py:135 one initial path
     }
 
-    // Decode the FPW frames whose channel LLRs are in wm.chan.  fmask/fval (FORCED): per-frame masks over
-    // phases -- bit phi of fmask set <=> u_phi is forced to bit phi of fval (scl.py:138-144,155-161).
+    // Decode the FPW frames of this warp; `chanf` = this lane's frame's channel row (N floats, stride 1).
+    // fmask/fval (FORCED): per-frame masks over phases -- bit phi of fmask set <=> u_phi is forced to bit phi of
+    // fval (scl.py:138-144,155-161).
     static __device__ __forceinline__ void run(const Code& code, const WarpMem<MP>& wm, PathT& p, int lane,
-                                               const uint32_t (&fmask)[XW], const uint32_t (&fval)[XW], uint32_t& flags) {
+                                               const float* chanf, const uint32_t (&fmask)[XW],
+                                               const uint32_t (&fval)[XW], uint32_t& flags) {
         const int N = code.N;
         const uint32_t M = (uint32_t)code.M;
         const int slot = lane & (MP - 1), gbase = lane & ~(MP - 1);
+        uint32_t* hs = reinterpret_cast<uint32_t*>(wm.xchg + 64);   // [32][2] high key words by rank (near-tie test)
         uint32_t tie = 0;
         uint32_t cur_info = 0, cur_fm = 0, cur_fv = 0;   // word phi/32 of the info / force masks
+        float a = 0.f, b = 0.f;                          // height-1 pair of the current phase pair
         for (int phi = 0; phi < N; ++phi) {
             if ((phi & 31) == 0) {
                 cur_info = code.info_mask[phi >> 5];
@@ -103,8 +135,12 @@ struct ListDecoder {
                     for (int k = 0; k < XW; ++k) if (k == (phi >> 5)) { cur_fm = fmask[k]; cur_fv = fval[k]; }
                 }
             }
+            const bool odd = phi & 1;
             float L = 0.f;
-            if (p.alive) L = leaf_llr(code, wm, p, phi, lane);
+            if (p.alive) {
+                if (!odd) { pair_llr(code, wm, p, phi, lane, chanf, a, b); L = f_op(a, b); }
+                else L = g_op(a, b, p.bw[0] & 1u);               // u_{phi-1} sits in the height-0 field
+            }
             const bool is_info = (cur_info >> (phi & 31)) & 1u;
             const bool is_forced = FORCED && is_info && ((cur_fm >> (phi & 31)) & 1u);
             const uint32_t forced_val = (cur_fv >> (phi & 31)) & 1u;
@@ -131,31 +167,39 @@ struct ListDecoder {
                     p.m = pick1 ? m1 : m0;
                     bit = pick1 ? 1u : 0u;
                 } else {
-                    const unsigned long long dead = ~0ull;
                     if (!is_info) {
                         // frozen phase (scl.py:149-153): one child per path.  The reference re-sorts here too (:173),
                         // but a rank is only ever used as the tie-break between EXACTLY equal metrics, so the
-                        // re-ranking is deferred to the next prune / the final ordering (rank_final below).
+                        // re-ranking is deferred to the next prune / the final ordering below.
                         if (a0) p.m = m0;
                         bit = 0;
                     } else {
+                        // Keys: IEEE bits of the (non-negative) fp64 metric with the stable-sort tie-break 2*rank+bit in
+                        // the 4 lowest mantissa bits.  They order identically as integers and as doubles, so the rank
+                        // compares run on the otherwise idle FP64 pipe (one DSETP each); a dead candidate is NaN.
+                        const unsigned long long dead = ~0ull;
                         const unsigned long long k0 = a0 ? (((unsigned long long)__double_as_longlong(m0) & ~15ull) | (2u * p.r)) : dead;
                         const unsigned long long k1 = a1 ? (((unsigned long long)__double_as_longlong(m1) & ~15ull) | (2u * p.r + 1u)) : dead;
                         reinterpret_cast<ulonglong2*>(wm.xchg)[lane] = make_ulonglong2(k0, k1);
+                        *reinterpret_cast<uint2*>(hs + 2 * lane) = make_uint2(0xffffffffu, 0xffffffffu);
                         __syncwarp();
-                        uint32_t rank0 = 0, rank1 = 0, cnt0 = 0, cnt1 = 0;
-                        const uint32_t h0 = (uint32_t)(k0 >> 32), h1 = (uint32_t)(k1 >> 32);
+                        const double d0 = __longlong_as_double((long long)k0), d1 = __longlong_as_double((long long)k1);
+                        uint32_t rank0 = 0, rank1 = 0;
 #pragma unroll
                         for (int j = 0; j < MP; ++j) {
                             const ulonglong2 o = reinterpret_cast<const ulonglong2*>(wm.xchg)[gbase + j];
-                            const uint32_t ox = (uint32_t)(o.x >> 32), oy = (uint32_t)(o.y >> 32);
-                            rank0 += (o.x < k0) + (o.y < k0);
-                            rank1 += (o.x < k1) + (o.y < k1);
-                            cnt0 += ((uint32_t)(ox - h0 + 2u) <= 4u) + ((uint32_t)(oy - h0 + 2u) <= 4u);
-                            cnt1 += ((uint32_t)(ox - h1 + 2u) <= 4u) + ((uint32_t)(oy - h1 + 2u) <= 4u);
+                            const double ox = __longlong_as_double((long long)o.x), oy = __longlong_as_double((long long)o.y);
+                            rank0 += (ox < d0) + (oy < d0);
+                            rank1 += (ox < d1) + (oy < d1);
                         }
                         const bool s0 = a0 && rank0 < M, s1 = a1 && rank1 < M;   // scl.py:174 keep the M best
-                        if ((s0 && cnt0 >= 2) || (s1 && cnt1 >= 2)) tie = 1;
+                        // near-tie test on rank-sorted neighbours: a kept candidate and its successor within ~1e-6 relative
+                        const uint32_t h0 = (uint32_t)(k0 >> 32), h1 = (uint32_t)(k1 >> 32);
+                        if (a0) hs[2 * gbase + rank0] = h0;
+                        if (a1) hs[2 * gbase + rank1] = h1;
+                        __syncwarp();
+                        if (s0 && rank0 + 1 < 2 * MP && (uint32_t)(hs[2 * gbase + rank0 + 1] - h0) <= 2u) tie = 1;
+                        if (s1 && rank1 + 1 < 2 * MP && (uint32_t)(hs[2 * gbase + rank1 + 1] - h1) <= 2u) tie = 1;
                         const bool dbl = s0 && s1, fre = !s0 && !s1;
                         const uint32_t dm = (__ballot_sync(kFull, dbl) >> gbase) & GM;
                         const uint32_t fm = (__ballot_sync(kFull, fre) >> gbase) & GM;
@@ -175,22 +219,28 @@ struct ListDecoder {
                         for (int k = 0; k < BW; ++k) b2[k] = __shfl_sync(kFull, p.bw[k], src);
                         const double m2 = __shfl_sync(kFull, m1, src);
                         const uint32_t r2 = __shfl_sync(kFull, rank1, src);
+                        float a2 = a, bb2 = b;
+                        if (!odd) { a2 = __shfl_sync(kFull, a, src); bb2 = __shfl_sync(kFull, b, src); }
                         if (take) {
                             p.P = P2;
 #pragma unroll
                             for (int k = 0; k < BW; ++k) p.bw[k] = b2[k];
                             p.m = m2; p.r = r2; bit = 1; p.alive = true;
+                            a = a2; b = bb2;
                         } else if (s0) { p.m = m0; p.r = rank0; bit = 0; }
                         else if (s1) { p.m = m1; p.r = rank1; bit = 1; }
                         else p.alive = false;
                     }
                 }
             }
-            if (p.alive) set_bit(code, p, phi, bit);
+            if (p.alive) {
+                if (!odd) p.bw[0] = (p.bw[0] & ~1u) | bit;       // height-0 left buffer
+                else set_bit_odd(code, p, phi, bit);
+            }
             if constexpr (MP > 1) __syncwarp();
         }
         // final list order = metric order (scl.py:173-174,183-188), ties by the last computed rank
-        if constexpr (MP > 1) {
+        if constexpr (MP > 1 && METRIC) {
             const unsigned long long kf = p.alive ? (((unsigned long long)__double_as_longlong(p.m) & ~15ull) | p.r) : ~0ull;
             wm.xchg[lane] = kf;
             __syncwarp();
@@ -212,23 +262,32 @@ struct ListDecoder {
     // the values a path saw during list decoding (scl.py:159,167 info_llrs), recomputed instead of copied.
     template <typename Sink>
     static __device__ __forceinline__ void replay(const Code& code, const WarpMem<MP>& wm, int lane, bool active,
-                                                  const uint32_t (&u)[XW], Sink&& sink) {
+                                                  const float* chanf, const uint32_t (&u)[XW], Sink&& sink) {
         PathT q;
         init(q, lane, true);
         q.alive = active;
         q.P = (lane & (MP - 1)) * 0x11111111u;
         int j = 0;
         uint32_t cur_info = 0, cur_u = 0;
+        float a = 0.f, b = 0.f;
         for (int phi = 0; phi < code.N; ++phi) {
             if ((phi & 31) == 0) {
                 cur_info = code.info_mask[phi >> 5];
 #pragma unroll
                 for (int k = 0; k < XW; ++k) if (k == (phi >> 5)) cur_u = u[k];
             }
+            const bool odd = phi & 1;
             float L = 0.f;
-            if (active) L = leaf_llr(code, wm, q, phi, lane);
+            if (active) {
+                if (!odd) { pair_llr(code, wm, q, phi, lane, chanf, a, b); L = f_op(a, b); }
+                else L = g_op(a, b, q.bw[0] & 1u);
+            }
             if ((cur_info >> (phi & 31)) & 1u) { if (active) sink(j, L); ++j; }
-            if (active) set_bit(code, q, phi, (cur_u >> (phi & 31)) & 1u);
+            const uint32_t bit = (cur_u >> (phi & 31)) & 1u;
+            if (active) {
+                if (!odd) q.bw[0] = (q.bw[0] & ~1u) | bit;
+                else set_bit_odd(code, q, phi, bit);
+            }
         }
     }
 };

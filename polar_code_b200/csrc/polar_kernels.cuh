@@ -26,49 +26,31 @@ struct DecodeArgs {
     uint32_t* best_words;        // [B,XWn]
     uint8_t* crc_ok;
     uint32_t* flags;
+    unsigned char* gscratch;     // per-warp global scratch (WarpMem::gbytes each)
 };
 
-// Load the channel LLRs of FPW consecutive frames into wm.chan ([f][N+1]); fuses NR de-rate-matching
-// (rate_match.py:19-39: mean of the repeats, -1.0 where nothing was sent) and the de-interleaver gather.
+// NR rate matching: stage the de-rate-matched + de-interleaved row of each of the warp's FPW frames in wm.chan
+// ([f][N+1], global scratch).  rate_match.py:19-39: mean of the repeats, -1.0 where nothing was sent;
+// interleaver.py:26-37: gather through rm_src.  (Plain rows are read in place from the caller's buffer.)
 template <int MP>
 __device__ __forceinline__ void load_channel(const Code& code, const Tables& tb, const WarpMem<MP>& wm, const float* llr,
                                              int in_len, int64_t frame0, int64_t B, int lane) {
     constexpr int FPW = 32 / MP;
     const int N = code.N, n = code.n;
-    if (tb.E == 0) {
-        // plain rows: FPW*N consecutive floats; issue the loads in batches of 8 so they overlap in flight
-        const int total = FPW * N;
-        const float* base = llr + frame0 * (int64_t)in_len;
-        const int64_t avail = (B - frame0) * (int64_t)N;     // floats that exist behind `base`
-        for (int e0 = 0; e0 < total; e0 += 32 * 8) {
-            float v[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int e = e0 + k * 32 + lane;
-                v[k] = (e < total && e < avail) ? __ldcs(base + e) : 0.f;
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int e = e0 + k * 32 + lane;
-                if (e < total) wm.chan[(e >> n) * (N + 1) + (e & (N - 1))] = v[k];
+    for (int e = lane; e < FPW * N; e += 32) {
+        const int f = e >> n, i = e & (N - 1);
+        const int64_t frame = frame0 + f;
+        float v = 0.f;
+        if (frame < B) {
+            const int p = tb.rm_src[i];
+            if (p >= 0) {
+                float acc = 0.f;
+                int cnt = 0;
+                for (int q = p; q < tb.E; q += N) { acc += llr[frame * (int64_t)in_len + q]; ++cnt; }
+                v = cnt ? acc / (float)cnt : -1.0f;
             }
         }
-    } else {
-        for (int e = lane; e < FPW * N; e += 32) {
-            const int f = e >> n, i = e & (N - 1);
-            const int64_t frame = frame0 + f;
-            float v = 0.f;
-            if (frame < B) {
-                const int p = tb.rm_src[i];
-                if (p >= 0) {
-                    float acc = 0.f;
-                    int cnt = 0;
-                    for (int q = p; q < tb.E; q += N) { acc += llr[frame * (int64_t)in_len + q]; ++cnt; }
-                    v = cnt ? acc / (float)cnt : -1.0f;
-                }
-            }
-            wm.chan[f * (N + 1) + i] = v;
-        }
+        wm.chan[f * (N + 1) + i] = v;
     }
     __syncwarp();
 }
@@ -141,8 +123,8 @@ __global__ void decode_kernel(const Code code, const Tables tb, const DecodeArgs
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpc = blockDim.x >> 5;
     WarpMem<MP> wm;
-    wm.carve(smem + (size_t)warp * WarpMem<MP>::bytes(code.N), code.N);
-    const int slot = lane & (MP - 1);
+    wm.carve(smem + (size_t)warp * WarpMem<MP>::bytes(code.N),
+             a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WarpMem<MP>::gbytes(code.N), code.N);
     const int K = code.K, M = code.M;
     const int xwn = code.N >= 32 ? code.N / 32 : 1;
     const int64_t ngroups = (a.B + FPW - 1) / FPW;
@@ -150,13 +132,18 @@ __global__ void decode_kernel(const Code code, const Tables tb, const DecodeArgs
         const int64_t frame0 = g * FPW;
         const int64_t frame = frame0 + lane / MP;
         const bool valid = frame < a.B;
-        load_channel<MP>(code, tb, wm, a.llr, a.in_len, frame0, a.B, lane);
+        const float* chanf;
+        if (tb.E == 0) chanf = a.llr + (valid ? frame : 0) * (int64_t)a.in_len;      // rows are decoded in place
+        else {
+            load_channel<MP>(code, tb, wm, a.llr, a.in_len, frame0, a.B, lane);
+            chanf = wm.chan + (lane / MP) * (code.N + 1);
+        }
         uint32_t flags = 0;
         uint32_t fmask[XW], fval[XW];
         if constexpr (FORCED) load_force<XW>(code, a.force, frame, valid, fmask, fval, flags);
         PathT p;
         Dec::init(p, lane, valid);
-        Dec::run(code, wm, p, lane, fmask, fval, flags);
+        Dec::run(code, wm, p, lane, chanf, fmask, fval, flags);
 
         // u-hat = x-hat * F^{(x)n}
         uint32_t u[XW];
@@ -177,11 +164,11 @@ __global__ void decode_kernel(const Code code, const Tables tb, const DecodeArgs
 
         if (a.info_llrs != nullptr) {
             float* dst = a.info_llrs + ((frame * M + p.r) * (int64_t)K);
-            Dec::replay(code, wm, lane, p.alive, u, [&](int j, float L) { dst[j] = L; });
+            Dec::replay(code, wm, lane, p.alive, chanf, u, [&](int j, float L) { dst[j] = L; });
             __syncwarp();
         }
         // stash u-hat words in the (now dead) tree area of the own slot for dynamic bit addressing
-        float* stash = wm.tree + lane;
+        float* stash = wm.scr + lane;
 #pragma unroll
         for (int k = 0; k < XW; ++k) if (k < xwn) stash[k * 32] = __uint_as_float(u[k]);
         if (p.alive) {
@@ -197,7 +184,6 @@ __global__ void decode_kernel(const Code code, const Tables tb, const DecodeArgs
             }
         }
         __syncwarp();
-        (void)slot;
     }
 }
 

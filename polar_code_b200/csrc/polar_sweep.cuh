@@ -83,6 +83,7 @@ struct SweepArgs {
     unsigned int* q_in_count;
     unsigned int* q_out_count;
     unsigned int q_capacity;
+    unsigned char* gscratch;       // per-warp global scratch (WarpMem::gbytes each)
 };
 
 template <int XW> struct DlEntry { DlEntryHdr h; uint32_t u[XW]; uint32_t tried[XW]; };
@@ -103,7 +104,7 @@ __device__ __forceinline__ void gen_channel(const Code& code, const Tables& tb, 
     const int N = code.N, K = code.K;
     const int xwn = N >= 32 ? N / 32 : 1;
     const int slot = lane & (MP - 1), gbase = lane & ~(MP - 1), fme = lane / MP;
-    uint32_t* scr = reinterpret_cast<uint32_t*>(wm.tree);      // per-lane column: scr[w*32 + lane]
+    uint32_t* scr = reinterpret_cast<uint32_t*>(wm.scr);       // per-lane column: scr[w*32 + lane]
     const uint2 key = make_uint2(cc.k0, cc.k1);
     const int pwn = (cc.kp + 31) / 32;
     // ---- payload -> CRC -> u -> x on the group leader ------------------------------------------------
@@ -346,7 +347,7 @@ struct Sweep {
             for (int q = 0; q < XW; ++q) if (q == k) w = b.u[q];
             a.best_words[idx * xwn + k] = w; }
         if (a.best_bits) {
-            float* stash = wm.tree + lane;
+            float* stash = wm.scr + lane;
 #pragma unroll
             for (int k = 0; k < XW; ++k) if (k < xwn) stash[k * 32] = __uint_as_float(b.u[k]);
             write_info_bits(code, tb, stash, a.best_bits + idx * (long long)code.K);
@@ -396,7 +397,8 @@ __global__ void sweep_kernel(const Code code, const Tables tb, const SweepArgs a
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     WarpMem<MP> wm;
-    wm.carve(smem + (size_t)warp * WarpMem<MP>::bytes(code.N), code.N);
+    wm.carve(smem + (size_t)warp * WarpMem<MP>::bytes(code.N),
+             a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WarpMem<MP>::gbytes(code.N), code.N);
     const bool leader = (lane & (MP - 1)) == 0;
     uint32_t acc[cNum];
 #pragma unroll
@@ -419,7 +421,8 @@ __global__ void sweep_kernel(const Code code, const Tables tb, const SweepArgs a
         uint32_t fm[XW], fv[XW];
         PathT p;
         S::DecU::init(p, lane, valid);
-        S::DecU::run(code, wm, p, lane, fm, fv, flags);
+        const float* chanf = wm.chan + (lane / MP) * (code.N + 1);
+        S::DecU::run(code, wm, p, lane, chanf, fm, fv, flags);
         typename S::Best b;
         S::pick_best(code, tb, p, lane, flags, b);
         bool need = false;
@@ -469,7 +472,8 @@ __global__ void dl_round_kernel(const Code code, const Tables tb, const SweepArg
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     WarpMem<MP> wm;
-    wm.carve(smem + (size_t)warp * WarpMem<MP>::bytes(code.N, code.K), code.N);
+    wm.carve(smem + (size_t)warp * WarpMem<MP>::bytes(code.N, code.K),
+             a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WarpMem<MP>::gbytes(code.N), code.N);
     const int slot = lane & (MP - 1), fme = lane / MP;
     const bool leader = slot == 0;
     const int K = code.K;
@@ -505,7 +509,8 @@ __global__ void dl_round_kernel(const Code code, const Tables tb, const SweepArg
         }
         // |L0| of the reference path (flip.py:102,133): replay it and keep the info-phase leaf LLRs
         float* ab = wm.absl + fme * (K + 1);
-        S::DecU::replay(code, wm, lane, valid, u_ref, [&](int j, float L) { if (leader) ab[j] = fabsf(L); });
+        const float* chanf = wm.chan + fme * (code.N + 1);
+        S::DecU::replay(code, wm, lane, valid, chanf, u_ref, [&](int j, float L) { if (leader) ab[j] = fabsf(L); });
         __syncwarp();
         // rank_indices (flip.py:104-108): first untried index of argsort(|L0| @ beta) = argmin over untried
         double m1 = 1e300, m2 = 1e300;
@@ -568,7 +573,7 @@ __global__ void dl_round_kernel(const Code code, const Tables tb, const SweepArg
         uint32_t flags = 0;
         PathT p;
         S::DecF::init(p, lane, valid);
-        S::DecF::run(code, wm, p, lane, fm, fv, flags);        // retry_with_flip (flip.py:37-62)
+        S::DecF::run(code, wm, p, lane, chanf, fm, fv, flags); // retry_with_flip (flip.py:37-62)
         typename S::Best b;
         S::pick_best(code, tb, p, lane, flags | eflags, b);
         bool need = false;
@@ -592,7 +597,8 @@ __global__ void channel_kernel(const Code code, const Tables tb, const SweepArgs
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     WarpMem<MP> wm;
-    wm.carve(smem + (size_t)warp * WarpMem<MP>::bytes(code.N), code.N);
+    wm.carve(smem + (size_t)warp * WarpMem<MP>::bytes(code.N),
+             a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WarpMem<MP>::gbytes(code.N), code.N);
     const long long ngroups = (a.n_frames + FPW - 1) / FPW;
     for (long long g = (long long)blockIdx.x * wpc + warp; g < ngroups; g += (long long)gridDim.x * wpc) {
         const long long idx = g * FPW + lane / MP;
@@ -602,7 +608,7 @@ __global__ void channel_kernel(const Code code, const Tables tb, const SweepArgs
         uint32_t unc;
         gen_channel<MP, XW>(code, tb, a.cc, wm, my_frame, lane, u_sent, unc, true, llr, a.frame_begin);
         if (msg && valid && (lane & (MP - 1)) == 0) {
-            float* stash = wm.tree + lane;
+            float* stash = wm.scr + lane;
             const int xwn = code.N >= 32 ? code.N / 32 : 1;
 #pragma unroll
             for (int k = 0; k < XW; ++k) if (k < xwn) stash[k * 32] = __uint_as_float(u_sent[k]);
