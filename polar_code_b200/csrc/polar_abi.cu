@@ -109,6 +109,7 @@ struct pb200_engine {
     int K = 0;
     Tables tb{};
     int16_t* d_info_pos = nullptr;
+    uint32_t* d_info_mask = nullptr;
     uint32_t* d_crc_tab = nullptr;
     int16_t* d_rm_src = nullptr;
     int16_t* d_tx_src = nullptr;   // NR transmit gather: tx[e] = code[tx_src[e]] or pad (-1)
@@ -226,11 +227,13 @@ extern "C" int pb200_create(pb200_engine** out, int device, int N, const int32_t
     cudaError_t ce;
     if ((ce = up((void**)&e->d_info_pos, pos16.data(), pos16.size() * 2)) != cudaSuccess ||
         (ce = up((void**)&e->d_crc_tab, crc_tab.data(), crc_tab.size() * 4)) != cudaSuccess ||
+        (ce = up((void**)&e->d_info_mask, e->code.info_mask, sizeof e->code.info_mask)) != cudaSuccess ||
         (ce = up((void**)&e->d_rm_src, rm.data(), rm.size() * 2)) != cudaSuccess) {
         pb200_destroy(e);
         return fail(PB200_ECUDA, "table upload failed: %s", cudaGetErrorString(ce));
     }
     e->tb.info_pos = e->d_info_pos;
+    e->tb.info_mask = e->d_info_mask;
     e->tb.crc_tab = e->d_crc_tab;
     e->tb.rm_src = e->d_rm_src;
     e->tb.E = 0;
@@ -243,7 +246,7 @@ extern "C" int pb200_create(pb200_engine** out, int device, int N, const int32_t
 extern "C" void pb200_destroy(pb200_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
-    cudaFree(e->d_info_pos); cudaFree(e->d_crc_tab); cudaFree(e->d_rm_src); cudaFree(e->d_tx_src); cudaFree(e->d_enc_tab);
+    cudaFree(e->d_info_pos); cudaFree(e->d_info_mask); cudaFree(e->d_crc_tab); cudaFree(e->d_rm_src); cudaFree(e->d_tx_src); cudaFree(e->d_enc_tab);
     cudaFree(e->d_scratch); cudaFree(e->d_rm_dst); cudaFree(e->d_q[0]); cudaFree(e->d_q[1]); cudaFree(e->d_q_counts);
     for (int i = 0; i < 3; ++i) {
         if (e->hs[i]) cudaStreamDestroy(e->hs[i]);

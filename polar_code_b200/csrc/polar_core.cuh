@@ -46,7 +46,7 @@ constexpr uint32_t kFull = 0xffffffffu;
 struct Code {
     int N, n, K, M;                   // code length, log2, info bits, list size (M <= MP)
     int crc_deg;                      // 0 = no CRC
-    uint32_t info_mask[kMaxWords];    // bit phi set <=> phase phi is an information bit
+    uint32_t info_mask[kMaxWords];    // bit phi set <=> phase phi is an information bit (index it with STATIC indices only)
 };
 
 __device__ __forceinline__ float f_op(float a, float b) {
@@ -63,7 +63,6 @@ __device__ __forceinline__ float g_op(float a, float b, uint32_t bit) {
 // log(1+exp(-|L|)) -- shared part of both softplus branches (scl.py:102-105).
 __device__ __forceinline__ float softplus_tail(float L) { return log1pf(expf(-fabsf(L))); }
 
-__device__ __forceinline__ bool info_bit(const Code& c, int phi) { return (c.info_mask[phi >> 5] >> (phi & 31)) & 1u; }
 
 // ---------------------------------------------------------------------------
 // Per-warp memory view.

@@ -14,15 +14,22 @@ struct ListDecoder {
     static constexpr int FPW = 32 / MP;
     static constexpr uint32_t GM = (MP >= 32) ? 0xffffffffu : ((1u << MP) - 1u);
 
-    // word w of the left-child bit buffer of height h (runtime h; warp-uniform selects)
-    static __device__ __forceinline__ uint32_t height_word(const uint32_t (&bw)[BW], int h, int w) {
-        if (h < 5) return bw[0] >> ((1 << h) - 1);
-        if (h == 5) return bw[1];
-        uint32_t r = 0;
-        const int first = (h == 6) ? 2 : (h == 7) ? 4 : 8;
+    static constexpr int TW = ((1 << LOGMAX) / 64) > 0 ? ((1 << LOGMAX) / 64) : 1;   // words of the tallest left buffer
+
+    // left-child bit buffer of (runtime, warp-uniform) height h as words tw[0..]; every register index is static
+    static __device__ __forceinline__ void height_words(const uint32_t (&bw)[BW], int h, uint32_t (&tw)[TW]) {
 #pragma unroll
-        for (int k = 2; k < BW; ++k) if (k == first + w) r = bw[k];
-        return r;
+        for (int k = 0; k < TW; ++k) tw[k] = 0;
+        switch (h) {
+            case 5: tw[0] = bw[1]; break;
+            case 6: if constexpr (TW >= 2) { tw[0] = bw[2]; tw[1] = bw[3]; } break;
+            case 7: if constexpr (TW >= 4 && BW >= 8) { tw[0] = bw[4]; tw[1] = bw[5]; tw[2] = bw[6]; tw[3] = bw[7]; } break;
+            case 8: if constexpr (TW >= 8 && BW >= 16) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) tw[k] = bw[8 + k];
+            } break;
+            default: tw[0] = bw[0] >> ((1 << (h & 7)) - 1); break;   // h < 5: field of word 0
+        }
     }
 
     // height n-1 from the channel row: f at phi = 0, g (left bits of height n-1) at phi = N/2.  Runtime-sized loop;
@@ -38,16 +45,26 @@ struct ListDecoder {
         }
         float* dst = ((h >= kHSplit) ? wm.tg : wm.ts) + lane + (half - 2) * 32;
         const int nw = half >= 32 ? half / 32 : 1, per = half >= 32 ? 32 : half;
-        for (int w = 0; w < nw; ++w) {
-            const float* x = chanf + w * 32;
-            float* d = dst + w * 32 * 32;
-            if (!is_g) {
+        if (!is_g) {
+            for (int i = 0; i < half; i += 8) {
+                float v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = (i + k < half) ? f_op(chanf[i + k], chanf[i + k + half]) : 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) if (i + k < half) dst[(i + k) * 32] = v[k];
+            }
+        } else {
+            uint32_t tw[TW];
+            height_words(p.bw, h, tw);
+#pragma unroll
+            for (int w = 0; w < TW; ++w) {
+                if (w < nw) {
+                    const uint32_t bits = tw[w];
+                    const float* x = chanf + w * 32;
+                    float* d = dst + w * 32 * 32;
 #pragma unroll 8
-                for (int j = 0; j < per; ++j) d[j * 32] = f_op(x[j], x[j + half]);
-            } else {
-                const uint32_t bits = height_word(p.bw, h, w);
-#pragma unroll 8
-                for (int j = 0; j < per; ++j) d[j * 32] = g_op(x[j], x[j + half], (bits >> j) & 1u);
+                    for (int j = 0; j < per; ++j) d[j * 32] = g_op(x[j], x[j + half], (bits >> j) & 1u);
+                }
             }
         }
     }
@@ -117,8 +134,8 @@ struct ListDecoder {
     // Decode the FPW frames of this warp; `chanf` = this lane's frame's channel row (N floats, stride 1).
     // fmask/fval (FORCED): per-frame masks over phases -- bit phi of fmask set <=> u_phi is forced to bit phi of
     // fval (scl.py:138-144,155-161).
-    static __device__ __forceinline__ void run(const Code& code, const WarpMem<MP>& wm, PathT& p, int lane,
-                                               const float* chanf, const uint32_t (&fmask)[XW],
+    static __device__ __forceinline__ void run(const Code& code, const uint32_t* __restrict__ imask, const WarpMem<MP>& wm, PathT& p,
+                                               int lane, const float* chanf, const uint32_t (&fmask)[XW],
                                                const uint32_t (&fval)[XW], uint32_t& flags) {
         const int N = code.N;
         const uint32_t M = (uint32_t)code.M;
@@ -129,7 +146,7 @@ struct ListDecoder {
         float a = 0.f, b = 0.f;                          // height-1 pair of the current phase pair
         for (int phi = 0; phi < N; ++phi) {
             if ((phi & 31) == 0) {
-                cur_info = code.info_mask[phi >> 5];
+                cur_info = __ldg(imask + (phi >> 5));     // (a dynamic index into the by-value Code would force it into local memory)
                 if constexpr (FORCED) {
 #pragma unroll
                     for (int k = 0; k < XW; ++k) if (k == (phi >> 5)) { cur_fm = fmask[k]; cur_fv = fval[k]; }
@@ -261,8 +278,8 @@ struct ListDecoder {
     // SC pass along the known bits `u` (own slot only), reporting the leaf LLR of every information phase:
     // the values a path saw during list decoding (scl.py:159,167 info_llrs), recomputed instead of copied.
     template <typename Sink>
-    static __device__ __forceinline__ void replay(const Code& code, const WarpMem<MP>& wm, int lane, bool active,
-                                                  const float* chanf, const uint32_t (&u)[XW], Sink&& sink) {
+    static __device__ __forceinline__ void replay(const Code& code, const uint32_t* __restrict__ imask, const WarpMem<MP>& wm, int lane,
+                                                  bool active, const float* chanf, const uint32_t (&u)[XW], Sink&& sink) {
         PathT q;
         init(q, lane, true);
         q.alive = active;
@@ -272,7 +289,7 @@ struct ListDecoder {
         float a = 0.f, b = 0.f;
         for (int phi = 0; phi < code.N; ++phi) {
             if ((phi & 31) == 0) {
-                cur_info = code.info_mask[phi >> 5];
+                cur_info = __ldg(imask + (phi >> 5));
 #pragma unroll
                 for (int k = 0; k < XW; ++k) if (k == (phi >> 5)) cur_u = u[k];
             }

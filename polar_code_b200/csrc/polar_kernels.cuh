@@ -7,6 +7,7 @@ namespace pb {
 // Device-side tables of one engine (all read-only).
 struct Tables {
     const int16_t* info_pos;     // [K] phase index of info bit j
+    const uint32_t* info_mask;   // [16] device copy of Code::info_mask for dynamic indexing
     const uint32_t* crc_tab;     // [N/4][16] syndrome contribution of nibble value v at nibble position p
     const int16_t* rm_src;       // [N] NR: position in the de-rate-matched vector feeding internal LLR i, -1 = 0.0
     int E;                       // NR transmitted length (0 = off)
@@ -143,7 +144,7 @@ __global__ void decode_kernel(const Code code, const Tables tb, const DecodeArgs
         if constexpr (FORCED) load_force<XW>(code, a.force, frame, valid, fmask, fval, flags);
         PathT p;
         Dec::init(p, lane, valid);
-        Dec::run(code, wm, p, lane, chanf, fmask, fval, flags);
+        Dec::run(code, tb.info_mask, wm, p, lane, chanf, fmask, fval, flags);
 
         // u-hat = x-hat * F^{(x)n}
         uint32_t u[XW];
@@ -164,7 +165,7 @@ __global__ void decode_kernel(const Code code, const Tables tb, const DecodeArgs
 
         if (a.info_llrs != nullptr) {
             float* dst = a.info_llrs + ((frame * M + p.r) * (int64_t)K);
-            Dec::replay(code, wm, lane, p.alive, chanf, u, [&](int j, float L) { dst[j] = L; });
+            Dec::replay(code, tb.info_mask, wm, lane, p.alive, chanf, u, [&](int j, float L) { dst[j] = L; });
             __syncwarp();
         }
         // stash u-hat words in the (now dead) tree area of the own slot for dynamic bit addressing

@@ -422,7 +422,7 @@ __global__ void sweep_kernel(const Code code, const Tables tb, const SweepArgs a
         PathT p;
         S::DecU::init(p, lane, valid);
         const float* chanf = wm.chan + (lane / MP) * (code.N + 1);
-        S::DecU::run(code, wm, p, lane, chanf, fm, fv, flags);
+        S::DecU::run(code, tb.info_mask, wm, p, lane, chanf, fm, fv, flags);
         typename S::Best b;
         S::pick_best(code, tb, p, lane, flags, b);
         bool need = false;
@@ -510,7 +510,7 @@ __global__ void dl_round_kernel(const Code code, const Tables tb, const SweepArg
         // |L0| of the reference path (flip.py:102,133): replay it and keep the info-phase leaf LLRs
         float* ab = wm.absl + fme * (K + 1);
         const float* chanf = wm.chan + fme * (code.N + 1);
-        S::DecU::replay(code, wm, lane, valid, chanf, u_ref, [&](int j, float L) { if (leader) ab[j] = fabsf(L); });
+        S::DecU::replay(code, tb.info_mask, wm, lane, valid, chanf, u_ref, [&](int j, float L) { if (leader) ab[j] = fabsf(L); });
         __syncwarp();
         // rank_indices (flip.py:104-108): first untried index of argsort(|L0| @ beta) = argmin over untried
         double m1 = 1e300, m2 = 1e300;
@@ -573,7 +573,7 @@ __global__ void dl_round_kernel(const Code code, const Tables tb, const SweepArg
         uint32_t flags = 0;
         PathT p;
         S::DecF::init(p, lane, valid);
-        S::DecF::run(code, wm, p, lane, chanf, fm, fv, flags); // retry_with_flip (flip.py:37-62)
+        S::DecF::run(code, tb.info_mask, wm, p, lane, chanf, fm, fv, flags); // retry_with_flip (flip.py:37-62)
         typename S::Best b;
         S::pick_best(code, tb, p, lane, flags | eflags, b);
         bool need = false;
