@@ -15,7 +15,8 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 _CSRC = _PKG / "csrc"
 _OBJ = _CSRC / "obj"
-_LIB = _PKG / "libpolar_b200.so"
+_LIB = Path(os.environ["PB200_LIBRARY"]).resolve() if os.environ.get("PB200_LIBRARY") else _PKG / "libpolar_b200.so"
+_EXTRA = os.environ.get("PB200_DEFINES", "").split()      # experiment knobs, e.g. -DPB_HSPLIT=6 (default build: none)
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -52,14 +53,15 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: libpolar_b200.so must be built on a box with the CUDA toolkit")
-    _OBJ.mkdir(exist_ok=True)
+    obj_dir = _OBJ if not _EXTRA else _CSRC / ("obj_" + "_".join(x.strip("-").replace("=", "") for x in _EXTRA))
+    obj_dir.mkdir(exist_ok=True)
     hdr_time = max(h.stat().st_mtime for h in _headers())
 
     def compile_one(src: Path) -> Path:
-        obj = _OBJ / (src.stem + ".o")
+        obj = obj_dir / (src.stem + ".o")
         if not force and obj.exists() and obj.stat().st_mtime > max(src.stat().st_mtime, hdr_time):
             return obj
-        cmd = [nvcc, *NVCC_FLAGS, "-c", "-o", str(obj), str(src)]
+        cmd = [nvcc, *NVCC_FLAGS, *_EXTRA, "-c", "-o", str(obj), str(src)]
         if verbose:
             cmd[1:1] = ["-Xptxas", "-v"]
             print(" ".join(cmd), flush=True)

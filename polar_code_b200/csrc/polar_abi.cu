@@ -298,12 +298,13 @@ static const void* pick_decode(int n, int MP, bool forced, bool metric) {
 
 static int round_mp(int M) { return M <= 1 ? 1 : M <= 2 ? 2 : M <= 4 ? 4 : 8; }
 
+// per-warp global scratch; sized for the smallest split (HS = 5) so every kernel of the engine fits
 static size_t warp_gbytes(int MP, int N) {
     switch (MP) {
-        case 1: return WarpMem<1>::gbytes(N);
-        case 2: return WarpMem<2>::gbytes(N);
-        case 4: return WarpMem<4>::gbytes(N);
-        default: return WarpMem<8>::gbytes(N);
+        case 1: return WarpMem<1, 5>::gbytes(N);
+        case 2: return WarpMem<2, 5>::gbytes(N);
+        case 4: return WarpMem<4, 5>::gbytes(N);
+        default: return WarpMem<8, 5>::gbytes(N);
     }
 }
 
@@ -319,7 +320,16 @@ static int ensure_scratch(pb200_engine* e, size_t warps, int MP) {
     return PB200_OK;
 }
 
-static size_t warp_bytes(int MP, int N, int xk) {
+// shared bytes per warp; round = DL-SCL round kernel (HS = 5), otherwise the kernel's default split
+static size_t warp_bytes(int MP, int N, int xk, bool round = false) {
+    if (round) {
+        switch (MP) {
+            case 1: return WarpMem<1, 5>::bytes(N, xk);
+            case 2: return WarpMem<2, 5>::bytes(N, xk);
+            case 4: return WarpMem<4, 5>::bytes(N, xk);
+            default: return WarpMem<8, 5>::bytes(N, xk);
+        }
+    }
     switch (MP) {
         case 1: return WarpMem<1>::bytes(N, xk);
         case 2: return WarpMem<2>::bytes(N, xk);

@@ -121,7 +121,7 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
             CUDA_TRY(cudaLaunchKernel(base, dim3(grid), dim3(kb.wpc * 32), args, kb.smem, st));
         }
         if (a.retries > 0) {
-            rc = choose_cfg(e, round, MP, 5, warp_bytes(MP, code.N, code.K), &kr);
+            rc = choose_cfg(e, round, MP, 5, warp_bytes(MP, code.N, code.K, true), &kr);
             if (rc) return rc;
             const long long rgroups = (nf + fpw - 1) / fpw;
             const long long rwant = (rgroups + kr.wpc - 1) / kr.wpc;
@@ -200,7 +200,7 @@ extern "C" int pb200_channel_batch(pb200_engine* e, const pb200_sweep_cfg* c, ui
     a.frame_begin = c->frame_begin; a.n_frames = c->n_frames;
     fill_chan(e, c, &a.cc);
     a.cc.include_uncoded = 0;
-    const size_t wb = WarpMem<4>::bytes(e->code.N);
+    const size_t wb = WarpMem<4, 5>::bytes(e->code.N);
     const int wpc = 4;
     const long long groups = (c->n_frames + 7) / 8;
     const int grid = (int)std::max<long long>(1, std::min<long long>((groups + wpc - 1) / wpc, (long long)e->sms * 8));

@@ -60,8 +60,24 @@ __device__ __forceinline__ float g_op(float a, float b, uint32_t bit) {
     return b + __uint_as_float(__float_as_uint(a) ^ (bit << 31));
 }
 
-// log(1+exp(-|L|)) -- shared part of both softplus branches (scl.py:102-105).
-__device__ __forceinline__ float softplus_tail(float L) { return log1pf(expf(-fabsf(L))); }
+// log(1+exp(-|L|)) -- the part both softplus branches share (scl.py:102-105; numpy logaddexp = max + log1p(exp(-|d|))).
+// t = exp(-|L|) in (0,1]; log1p(t) = t*q(t) with q a degree-9 near-minimax polynomial of log1p(t)/t on [0,1]
+// (Chebyshev-node fit, max relative error 5e-9; 1.6e-7 after fp32 Horner) -- as accurate as log1pf(expf()) in
+// fp32 (2.9e-7) at a third of the instructions; the t*q form keeps full relative accuracy as t -> 0.
+__device__ __forceinline__ float softplus_tail(float L) {
+    const float t = __expf(-fabsf(L));
+    float q = -3.176057010e-03f;
+    q = fmaf(q, t, 1.954252722e-02f);
+    q = fmaf(q, t, -5.637361275e-02f);
+    q = fmaf(q, t, 1.054362379e-01f);
+    q = fmaf(q, t, -1.526966707e-01f);
+    q = fmaf(q, t, 1.966327426e-01f);
+    q = fmaf(q, t, -2.495161626e-01f);
+    q = fmaf(q, t, 3.332971050e-01f);
+    q = fmaf(q, t, -4.999989265e-01f);
+    q = fmaf(q, t, 9.999999947e-01f);
+    return q * t;
+}
 
 
 // ---------------------------------------------------------------------------
@@ -72,25 +88,30 @@ __device__ __forceinline__ float softplus_tail(float L) { return log1pf(expf(-fa
 //            resident warps (~16 KB each) stays L2-resident; moving the two big heights out of shared memory is
 //            what lifts occupancy from 11 to ~28 warps per SM for N = 128.
 // ---------------------------------------------------------------------------
-#ifndef PB_HSPLIT
-#define PB_HSPLIT 5
+#ifdef PB_LAUNCH_BOUNDS
+#define PB_LB __launch_bounds__(PB_LAUNCH_BOUNDS)
+#else
+#define PB_LB
 #endif
-constexpr int kHSplit = PB_HSPLIT;
+// Heights >= HS live in the global scratch.  HS = 6 keeps height 5 in shared memory (fewer L2 round trips) and
+// is best when registers, not shared memory, bound the occupancy (list kernels); HS = 5 maximises resident warps
+// (SC / M = 1 kernels, and the DL-SCL round kernels, which also hold the |L0| rows in shared memory).
+template <int MP> struct DefaultHS { static constexpr int value = (MP == 1) ? 5 : 6; };
 
-__host__ __device__ inline int tree_rows_shared(int N) {
+__host__ __device__ inline int tree_rows_shared(int N, int hs) {
     const int all = N >= 6 ? N - 2 : 4;                 // rows of heights 1..n-1 (at least 4 rows of scratch)
-    const int cap = (1 << kHSplit) - 2;
+    const int cap = (1 << hs) - 2;
     return all < cap ? all : cap;
 }
-__host__ __device__ inline int tree_rows_global(int N) {
+__host__ __device__ inline int tree_rows_global(int N, int hs) {
     const int all = N >= 6 ? N - 2 : 4;
-    const int cap = (1 << kHSplit) - 2;
+    const int cap = (1 << hs) - 2;
     return all > cap ? all - cap : 0;
 }
 
 constexpr int kXchgBytes = 32 * 16 + 32 * 2 * 4;   // candidate keys + rank-sorted high words
 
-template <int MP>
+template <int MP, int HS = DefaultHS<MP>::value>
 struct WarpMem {
     float* ts;            // shared tree base:  element (h,i), h <  HSPLIT, at ts[((2^h-2)+i)*32 + lane]
     float* tg;            // global tree base (pre-offset): element (h,i), h >= HSPLIT, at tg[((2^h-2)+i)*32 + lane]
@@ -99,13 +120,13 @@ struct WarpMem {
     unsigned long long* xchg;  // [32][2] candidate keys for the rank exchange / small per-frame scratch (shared)
     float* absl;          // [FPW][xk+1] DL-SCL only: |L0| of the reference path (flip.py:102) (shared)
     static constexpr int FPW = 32 / MP;
-    __host__ __device__ static size_t tree_bytes(int N) { return (size_t)tree_rows_shared(N) * 32 * 4; }
+    __host__ __device__ static size_t tree_bytes(int N) { return (size_t)tree_rows_shared(N, HS) * 32 * 4; }
     __host__ __device__ static size_t bytes(int N, int xk = 0) {          // shared bytes per warp
         size_t x = xk ? (((size_t)FPW * (xk + 1) * 4 + 15) & ~(size_t)15) : 0;
         return tree_bytes(N) + kXchgBytes + x;
     }
     __host__ __device__ static size_t gbytes(int N) {                     // global scratch bytes per warp
-        size_t t = (size_t)tree_rows_global(N) * 32 * 4;
+        size_t t = (size_t)tree_rows_global(N, HS) * 32 * 4;
         size_t ch = (((size_t)FPW * (N + 1) * 4) + 127) & ~(size_t)127;
         return t + ch;
     }
@@ -114,10 +135,10 @@ struct WarpMem {
         xchg = reinterpret_cast<unsigned long long*>(sbase + tree_bytes(N));
         absl = reinterpret_cast<float*>(sbase + tree_bytes(N) + kXchgBytes);
         float* g = reinterpret_cast<float*>(gbase);
-        tg = g - ((1 << kHSplit) - 2) * 32;
-        chan = g + (size_t)tree_rows_global(N) * 32;
+        tg = g - ((1 << HS) - 2) * 32;
+        chan = g + (size_t)tree_rows_global(N, HS) * 32;
         const int need = 3 * (N >= 32 ? N / 32 : 1);
-        scr = (tree_rows_shared(N) >= need) ? ts : g;
+        scr = (tree_rows_shared(N, HS) >= need) ? ts : g;
     }
 };
 
@@ -227,16 +248,17 @@ struct Path {
 // LLR tree evaluation.  Every routine stops at the height-1 pair (a, b): the two leaves of a phase pair are
 // f(a,b) and g(a,b,u_even) and never touch memory.
 // ---------------------------------------------------------------------------
-template <int MP, int LOGMAX>
+template <int MP, int LOGMAX, int HS>
 struct Tree {
+    using WM = WarpMem<MP, HS>;
     using PathT = Path<LOGMAX>;
     static constexpr int BW = PathT::BW;
 
-    template <int H> static __device__ __forceinline__ float* base(const WarpMem<MP>& wm) { return (H >= kHSplit) ? wm.tg : wm.ts; }
+    template <int H> static __device__ __forceinline__ float* base(const WM& wm) { return (H >= HS) ? wm.tg : wm.ts; }
 
     // 2^H register values (H >= 1) -> height-1 pair; heights H-1..2 are stored in the own slot
     template <int H>
-    static __device__ __forceinline__ void reg_chain(float (&v)[1 << H], const WarpMem<MP>& wm, int lane, float& a, float& b) {
+    static __device__ __forceinline__ void reg_chain(float (&v)[1 << H], const WM& wm, int lane, float& a, float& b) {
         if constexpr (H == 1) { a = v[0]; b = v[1]; }
         else {
             float w[(1 << H) / 2];
@@ -253,7 +275,7 @@ struct Tree {
     // Produce height H (>= 1) from height H+1 held at src[i*32] (tree, slot lane already folded into src) with
     // OP 0 = f, 1 = g using the left bits of height H; store it in the own slot; continue with f down to the pair.
     template <int H, int OP>
-    static __device__ __forceinline__ void produce(const float* src, const uint32_t (&bw)[BW], const WarpMem<MP>& wm, int lane,
+    static __device__ __forceinline__ void produce(const float* src, const uint32_t (&bw)[BW], const WM& wm, int lane,
                                                    float& a, float& b) {
         constexpr int S = 1 << H;
         float* own = base<H>(wm) + lane;
@@ -293,7 +315,7 @@ struct Tree {
 
     // f-chain from the own slot's height H (>= 2) down to the pair
     template <int H>
-    static __device__ __forceinline__ void chain_from(const uint32_t (&bw)[BW], const WarpMem<MP>& wm, int lane, float& a, float& b) {
+    static __device__ __forceinline__ void chain_from(const uint32_t (&bw)[BW], const WM& wm, int lane, float& a, float& b) {
         produce<H - 1, 0>(base<H>(wm) + lane + (((1 << H) - 2) * 32), bw, wm, lane, a, b);
     }
 };

@@ -5,10 +5,11 @@
 
 namespace pb {
 
-template <int MP, int LOGMAX, bool FORCED, bool METRIC>
+template <int MP, int LOGMAX, bool FORCED, bool METRIC, int HS = DefaultHS<MP>::value>
 struct ListDecoder {
     using PathT = Path<LOGMAX>;
-    using TreeT = Tree<MP, LOGMAX>;
+    using TreeT = Tree<MP, LOGMAX, HS>;
+    using WM = WarpMem<MP, HS>;
     static constexpr int BW = PathT::BW;
     static constexpr int XW = PathT::XW;
     static constexpr int FPW = 32 / MP;
@@ -34,7 +35,7 @@ struct ListDecoder {
 
     // height n-1 from the channel row: f at phi = 0, g (left bits of height n-1) at phi = N/2.  Runtime-sized loop;
     // `chanf` may point into the caller's LLR buffer (global) or into the staged row.
-    static __device__ __forceinline__ void top_level(const Code& code, const WarpMem<MP>& wm, const PathT& p, bool is_g, int lane,
+    static __device__ __forceinline__ void top_level(const Code& code, const WM& wm, const PathT& p, bool is_g, int lane,
                                                      const float* chanf, float& a, float& b) {
         const int half = code.N >> 1, h = code.n - 1;
         if (half == 2) {  // N = 4: height 1 is the pair itself
@@ -43,7 +44,7 @@ struct ListDecoder {
             a = v0; b = v1;
             return;
         }
-        float* dst = ((h >= kHSplit) ? wm.tg : wm.ts) + lane + (half - 2) * 32;
+        float* dst = ((h >= HS) ? wm.tg : wm.ts) + lane + (half - 2) * 32;
         const int nw = half >= 32 ? half / 32 : 1, per = half >= 32 ? 32 : half;
         if (!is_g) {
             for (int i = 0; i < half; i += 8) {
@@ -70,7 +71,7 @@ struct ListDecoder {
     }
 
     // height-1 pair (a, b) of this lane's path for the EVEN phase `phi` (lazy form of scl.py:64-82)
-    static __device__ __forceinline__ void pair_llr(const Code& code, const WarpMem<MP>& wm, PathT& p, int phi, int lane,
+    static __device__ __forceinline__ void pair_llr(const Code& code, const WM& wm, PathT& p, int phi, int lane,
                                                     const float* chanf, float& a, float& b) {
         const int n = code.n;
         const int slot = lane & (MP - 1), gbase = lane & ~(MP - 1);
@@ -86,7 +87,7 @@ struct ListDecoder {
             }
         } else {
             const uint32_t q = (p.P >> (4 * c)) & 0xfu;          // slot holding height c+1 (field c)
-            const float* src = ((c + 1 >= kHSplit) ? wm.tg : wm.ts) + (((2 << c) - 2) * 32) + gbase + q;
+            const float* src = ((c + 1 >= HS) ? wm.tg : wm.ts) + (((2 << c) - 2) * 32) + gbase + q;
             switch (c) {
 #define PB_CASE(CC) case CC: if constexpr (CC + 1 < LOGMAX) TreeT::template produce<CC, 1>(src, p.bw, wm, lane, a, b); break;
                 PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7)
@@ -134,7 +135,7 @@ struct ListDecoder {
     // Decode the FPW frames of this warp; `chanf` = this lane's frame's channel row (N floats, stride 1).
     // fmask/fval (FORCED): per-frame masks over phases -- bit phi of fmask set <=> u_phi is forced to bit phi of
     // fval (scl.py:138-144,155-161).
-    static __device__ __forceinline__ void run(const Code& code, const uint32_t* __restrict__ imask, const WarpMem<MP>& wm, PathT& p,
+    static __device__ __forceinline__ void run(const Code& code, const uint32_t* __restrict__ imask, const WM& wm, PathT& p,
                                                int lane, const float* chanf, const uint32_t (&fmask)[XW],
                                                const uint32_t (&fval)[XW], uint32_t& flags) {
         const int N = code.N;
@@ -278,7 +279,7 @@ struct ListDecoder {
     // SC pass along the known bits `u` (own slot only), reporting the leaf LLR of every information phase:
     // the values a path saw during list decoding (scl.py:159,167 info_llrs), recomputed instead of copied.
     template <typename Sink>
-    static __device__ __forceinline__ void replay(const Code& code, const uint32_t* __restrict__ imask, const WarpMem<MP>& wm, int lane,
+    static __device__ __forceinline__ void replay(const Code& code, const uint32_t* __restrict__ imask, const WM& wm, int lane,
                                                   bool active, const float* chanf, const uint32_t (&u)[XW], Sink&& sink) {
         PathT q;
         init(q, lane, true);

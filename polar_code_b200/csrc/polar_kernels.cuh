@@ -33,8 +33,8 @@ struct DecodeArgs {
 // NR rate matching: stage the de-rate-matched + de-interleaved row of each of the warp's FPW frames in wm.chan
 // ([f][N+1], global scratch).  rate_match.py:19-39: mean of the repeats, -1.0 where nothing was sent;
 // interleaver.py:26-37: gather through rm_src.  (Plain rows are read in place from the caller's buffer.)
-template <int MP>
-__device__ __forceinline__ void load_channel(const Code& code, const Tables& tb, const WarpMem<MP>& wm, const float* llr,
+template <int MP, typename WM>
+__device__ __forceinline__ void load_channel(const Code& code, const Tables& tb, const WM& wm, const float* llr,
                                              int in_len, int64_t frame0, int64_t B, int lane) {
     constexpr int FPW = 32 / MP;
     const int N = code.N, n = code.n;
@@ -115,17 +115,17 @@ __device__ __forceinline__ void load_force(const Code& code, const int8_t* force
     }
 }
 
-template <int MP, int LOGMAX, bool FORCED, bool METRIC>
-__global__ void decode_kernel(const Code code, const Tables tb, const DecodeArgs a) {
-    using Dec = ListDecoder<MP, LOGMAX, FORCED, METRIC>;
+template <int MP, int LOGMAX, bool FORCED, bool METRIC, int HS = DefaultHS<MP>::value>
+__global__ void PB_LB decode_kernel(const Code code, const Tables tb, const DecodeArgs a) {
+    using Dec = ListDecoder<MP, LOGMAX, FORCED, METRIC, HS>;
+    using WM = WarpMem<MP, HS>;
     using PathT = typename Dec::PathT;
     constexpr int FPW = 32 / MP, XW = PathT::XW;
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpc = blockDim.x >> 5;
-    WarpMem<MP> wm;
-    wm.carve(smem + (size_t)warp * WarpMem<MP>::bytes(code.N),
-             a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WarpMem<MP>::gbytes(code.N), code.N);
+    WM wm;
+    wm.carve(smem + (size_t)warp * WM::bytes(code.N), a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WM::gbytes(code.N), code.N);
     const int K = code.K, M = code.M;
     const int xwn = code.N >= 32 ? code.N / 32 : 1;
     const int64_t ngroups = (a.B + FPW - 1) / FPW;
@@ -136,7 +136,7 @@ __global__ void decode_kernel(const Code code, const Tables tb, const DecodeArgs
         const float* chanf;
         if (tb.E == 0) chanf = a.llr + (valid ? frame : 0) * (int64_t)a.in_len;      // rows are decoded in place
         else {
-            load_channel<MP>(code, tb, wm, a.llr, a.in_len, frame0, a.B, lane);
+            load_channel<MP, WM>(code, tb, wm, a.llr, a.in_len, frame0, a.B, lane);
             chanf = wm.chan + (lane / MP) * (code.N + 1);
         }
         uint32_t flags = 0;

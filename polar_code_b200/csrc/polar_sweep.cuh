@@ -96,8 +96,8 @@ enum { cFrames = 0, cSclFe, cSclBe, cDlFe, cDlBe, cUncFe, cUncBe, cDlWork, cNear
 // Leaves the channel LLRs in wm.chan, returns the transmitted u (all lanes of the group) and the frame's uncoded
 // bit-error count.  Scratch: the (not yet used) tree area.
 // ---------------------------------------------------------------------------------------------------
-template <int MP, int XW>
-__device__ __forceinline__ void gen_channel(const Code& code, const Tables& tb, const ChanCfg& cc, const WarpMem<MP>& wm,
+template <int MP, int XW, typename WM>
+__device__ __forceinline__ void gen_channel(const Code& code, const Tables& tb, const ChanCfg& cc, const WM& wm,
                                             long long my_frame, int lane, uint32_t (&u_sent)[XW], uint32_t& unc_err,
                                             bool want_chan, float* raw_out = nullptr, long long raw_base = 0) {
     constexpr int FPW = 32 / MP;
@@ -250,8 +250,8 @@ __device__ __forceinline__ void gen_channel(const Code& code, const Tables& tb, 
 
 
 // Gather-load of channel LLRs for arbitrary frame ids (LLR-in mode of the DL-SCL rounds).
-template <int MP>
-__device__ __forceinline__ void load_channel_ids(const Code& code, const Tables& tb, const WarpMem<MP>& wm, const float* llr,
+template <int MP, typename WM>
+__device__ __forceinline__ void load_channel_ids(const Code& code, const Tables& tb, const WM& wm, const float* llr,
                                                  int in_len, long long my_frame, long long frame_begin, int lane) {
     constexpr int FPW = 32 / MP;
     const int N = code.N;
@@ -280,10 +280,11 @@ __device__ __forceinline__ void load_channel_ids(const Code& code, const Tables&
     __syncwarp();
 }
 
-template <int MP, int LOGMAX>
+template <int MP, int LOGMAX, int HS>
 struct Sweep {
-    using DecU = ListDecoder<MP, LOGMAX, false, true>;
-    using DecF = ListDecoder<MP, LOGMAX, true, true>;
+    using DecU = ListDecoder<MP, LOGMAX, false, true, HS>;
+    using DecF = ListDecoder<MP, LOGMAX, true, true, HS>;
+    using WM = WarpMem<MP, HS>;
     using PathT = Path<LOGMAX>;
     static constexpr int XW = PathT::XW;
     static constexpr int FPW = 32 / MP;
@@ -327,7 +328,7 @@ struct Sweep {
     }
 
     // write the per-frame results of a finished DL-SCL frame (flip.py:137-141) / count it (run_fer_sweep.py:100-109)
-    static __device__ __forceinline__ void finish_dl(const Code& code, const Tables& tb, const SweepArgs& a, const WarpMem<MP>& wm, int lane,
+    static __device__ __forceinline__ void finish_dl(const Code& code, const Tables& tb, const SweepArgs& a, const WM& wm, int lane,
                                                      long long frame, const Best& b, uint32_t n_tried, const uint32_t (&u_sent)[XW], uint32_t (&acc)[cNum]) {
         const long long idx = frame - a.frame_begin;
         if (a.llr == nullptr) {
@@ -389,16 +390,16 @@ struct Sweep {
 // ---------------------------------------------------------------------------------------------------
 // Baseline pass: channel -> SCL(M) -> counters; failing frames go to the retry queue.
 // ---------------------------------------------------------------------------------------------------
-template <int MP, int LOGMAX>
-__global__ void sweep_kernel(const Code code, const Tables tb, const SweepArgs a) {
-    using S = Sweep<MP, LOGMAX>;
+template <int MP, int LOGMAX, int HS = DefaultHS<MP>::value>
+__global__ void PB_LB sweep_kernel(const Code code, const Tables tb, const SweepArgs a) {
+    using S = Sweep<MP, LOGMAX, HS>;
+    using WM = WarpMem<MP, HS>;
     using PathT = typename S::PathT;
     constexpr int FPW = 32 / MP, XW = S::XW;
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-    WarpMem<MP> wm;
-    wm.carve(smem + (size_t)warp * WarpMem<MP>::bytes(code.N),
-             a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WarpMem<MP>::gbytes(code.N), code.N);
+    WM wm;
+    wm.carve(smem + (size_t)warp * WM::bytes(code.N), a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WM::gbytes(code.N), code.N);
     const bool leader = (lane & (MP - 1)) == 0;
     uint32_t acc[cNum];
 #pragma unroll
@@ -413,9 +414,9 @@ __global__ void sweep_kernel(const Code code, const Tables tb, const SweepArgs a
         if (a.llr) {
 #pragma unroll
             for (int k = 0; k < XW; ++k) u_sent[k] = 0;
-            load_channel_ids<MP>(code, tb, wm, a.llr, a.in_len, my_frame, a.frame_begin, lane);
+            load_channel_ids<MP, WM>(code, tb, wm, a.llr, a.in_len, my_frame, a.frame_begin, lane);
         } else {
-            gen_channel<MP, XW>(code, tb, a.cc, wm, my_frame, lane, u_sent, unc, true);
+            gen_channel<MP, XW, WM>(code, tb, a.cc, wm, my_frame, lane, u_sent, unc, true);
         }
         uint32_t flags = 0;
         uint32_t fm[XW], fv[XW];
@@ -463,17 +464,17 @@ __global__ void sweep_kernel(const Code code, const Tables tb, const SweepArgs a
 // ---------------------------------------------------------------------------------------------------
 // One DL-SCL retry round over the compacted queue (flip.py:110-135).
 // ---------------------------------------------------------------------------------------------------
-template <int MP, int LOGMAX>
-__global__ void dl_round_kernel(const Code code, const Tables tb, const SweepArgs a) {
-    using S = Sweep<MP, LOGMAX>;
+template <int MP, int LOGMAX, int HS = 5>
+__global__ void PB_LB dl_round_kernel(const Code code, const Tables tb, const SweepArgs a) {
+    using S = Sweep<MP, LOGMAX, HS>;
+    using WM = WarpMem<MP, HS>;
     using PathT = typename S::PathT;
     using Entry = typename S::Entry;
     constexpr int FPW = 32 / MP, XW = S::XW;
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-    WarpMem<MP> wm;
-    wm.carve(smem + (size_t)warp * WarpMem<MP>::bytes(code.N, code.K),
-             a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WarpMem<MP>::gbytes(code.N), code.N);
+    WM wm;
+    wm.carve(smem + (size_t)warp * WM::bytes(code.N, code.K), a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WM::gbytes(code.N), code.N);
     const int slot = lane & (MP - 1), fme = lane / MP;
     const bool leader = slot == 0;
     const int K = code.K;
@@ -501,11 +502,11 @@ __global__ void dl_round_kernel(const Code code, const Tables tb, const SweepArg
         if (a.llr) {
 #pragma unroll
             for (int k = 0; k < XW; ++k) u_sent[k] = 0;
-            load_channel_ids<MP>(code, tb, wm, a.llr, a.in_len, my_frame, a.frame_begin, lane);
+            load_channel_ids<MP, WM>(code, tb, wm, a.llr, a.in_len, my_frame, a.frame_begin, lane);
         } else {
             ChanCfg cc = a.cc;
             cc.include_uncoded = 0;
-            gen_channel<MP, XW>(code, tb, cc, wm, my_frame, lane, u_sent, unc, true);
+            gen_channel<MP, XW, WM>(code, tb, cc, wm, my_frame, lane, u_sent, unc, true);
         }
         // |L0| of the reference path (flip.py:102,133): replay it and keep the info-phase leaf LLRs
         float* ab = wm.absl + fme * (K + 1);
@@ -596,9 +597,9 @@ __global__ void channel_kernel(const Code code, const Tables tb, const SweepArgs
     constexpr int XW = BitsCfg<LOGMAX>::XW;
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-    WarpMem<MP> wm;
-    wm.carve(smem + (size_t)warp * WarpMem<MP>::bytes(code.N),
-             a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WarpMem<MP>::gbytes(code.N), code.N);
+    using WM = WarpMem<MP, 5>;
+    WM wm;
+    wm.carve(smem + (size_t)warp * WM::bytes(code.N), a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WM::gbytes(code.N), code.N);
     const long long ngroups = (a.n_frames + FPW - 1) / FPW;
     for (long long g = (long long)blockIdx.x * wpc + warp; g < ngroups; g += (long long)gridDim.x * wpc) {
         const long long idx = g * FPW + lane / MP;
@@ -606,7 +607,7 @@ __global__ void channel_kernel(const Code code, const Tables tb, const SweepArgs
         const long long my_frame = valid ? a.frame_begin + idx : -1;
         uint32_t u_sent[XW];
         uint32_t unc;
-        gen_channel<MP, XW>(code, tb, a.cc, wm, my_frame, lane, u_sent, unc, true, llr, a.frame_begin);
+        gen_channel<MP, XW, WM>(code, tb, a.cc, wm, my_frame, lane, u_sent, unc, true, llr, a.frame_begin);
         if (msg && valid && (lane & (MP - 1)) == 0) {
             float* stash = wm.scr + lane;
             const int xwn = code.N >= 32 ? code.N / 32 : 1;
