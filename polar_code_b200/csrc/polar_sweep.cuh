@@ -391,7 +391,7 @@ struct Sweep {
 // Baseline pass: channel -> SCL(M) -> counters; failing frames go to the retry queue.
 // ---------------------------------------------------------------------------------------------------
 template <int MP, int LOGMAX, int HS = DefaultHS<MP>::value>
-__global__ void PB_LB sweep_kernel(const Code code, const Tables tb, const SweepArgs a) {
+__global__ void __launch_bounds__(768) sweep_kernel(const Code code, const Tables tb, const SweepArgs a) {
     using S = Sweep<MP, LOGMAX, HS>;
     using WM = WarpMem<MP, HS>;
     using PathT = typename S::PathT;
@@ -465,7 +465,7 @@ __global__ void PB_LB sweep_kernel(const Code code, const Tables tb, const Sweep
 // One DL-SCL retry round over the compacted queue (flip.py:110-135).
 // ---------------------------------------------------------------------------------------------------
 template <int MP, int LOGMAX, int HS = 5>
-__global__ void PB_LB dl_round_kernel(const Code code, const Tables tb, const SweepArgs a) {
+__global__ void __launch_bounds__(640) dl_round_kernel(const Code code, const Tables tb, const SweepArgs a) {
     using S = Sweep<MP, LOGMAX, HS>;
     using WM = WarpMem<MP, HS>;
     using PathT = typename S::PathT;
