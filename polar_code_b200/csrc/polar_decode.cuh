@@ -121,6 +121,11 @@ struct ListDecoder {
         }
     }
 
+    // r += (x < y) for doubles: one DSETP + one predicated IADD
+    static __device__ __forceinline__ void inc_if_lt(uint32_t& r, double x, double y) {
+        asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, %2;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(r) : "d"(x), "d"(y));
+    }
+
     static __device__ __forceinline__ void init(PathT& p, int lane, bool frame_valid) {
         p.P = 0;
 #pragma unroll
@@ -154,11 +159,10 @@ struct ListDecoder {
                 }
             }
             const bool odd = phi & 1;
-            float L = 0.f;
-            if (p.alive) {
-                if (!odd) { pair_llr(code, wm, p, phi, lane, chanf, a, b); L = f_op(a, b); }
-                else L = g_op(a, b, p.bw[0] & 1u);               // u_{phi-1} sits in the height-0 field
-            }
+            // Lanes without a live path run the same code on their own (unused) slot: no divergence, no merges.
+            float L;
+            if (!odd) { pair_llr(code, wm, p, phi, lane, chanf, a, b); L = f_op(a, b); }
+            else L = g_op(a, b, p.bw[0] & 1u);                   // u_{phi-1} sits in the height-0 field
             const bool is_info = (cur_info >> (phi & 31)) & 1u;
             const bool is_forced = FORCED && is_info && ((cur_fm >> (phi & 31)) & 1u);
             const uint32_t forced_val = (cur_fv >> (phi & 31)) & 1u;
@@ -189,7 +193,7 @@ struct ListDecoder {
                         // frozen phase (scl.py:149-153): one child per path.  The reference re-sorts here too (:173),
                         // but a rank is only ever used as the tie-break between EXACTLY equal metrics, so the
                         // re-ranking is deferred to the next prune / the final ordering below.
-                        if (a0) p.m = m0;
+                        p.m = m0;                                 // (a dead lane's metric is never read)
                         bit = 0;
                     } else {
                         // Keys: IEEE bits of the (non-negative) fp64 metric with the stable-sort tie-break 2*rank+bit in
@@ -207,8 +211,8 @@ struct ListDecoder {
                         for (int j = 0; j < MP; ++j) {
                             const ulonglong2 o = reinterpret_cast<const ulonglong2*>(wm.xchg)[gbase + j];
                             const double ox = __longlong_as_double((long long)o.x), oy = __longlong_as_double((long long)o.y);
-                            rank0 += (ox < d0) + (oy < d0);
-                            rank1 += (ox < d1) + (oy < d1);
+                            inc_if_lt(rank0, ox, d0); inc_if_lt(rank0, oy, d0);
+                            inc_if_lt(rank1, ox, d1); inc_if_lt(rank1, oy, d1);
                         }
                         const bool s0 = a0 && rank0 < M, s1 = a1 && rank1 < M;   // scl.py:174 keep the M best
                         // near-tie test on rank-sorted neighbours: a kept candidate and its successor within ~1e-6 relative
@@ -230,31 +234,24 @@ struct ListDecoder {
                             for (int i = 0; i < MP / 2; ++i) if (i < k) d &= d - 1;
                             if (d) { src = gbase + __ffs(d) - 1; take = true; }
                         }
-                        // the second child of a doubly-surviving path moves into a freed slot
-                        const uint32_t P2 = __shfl_sync(kFull, p.P, src);
-                        uint32_t b2[BW];
+                        // The second child of a doubly-surviving path moves into a freed slot.  Every lane reads from
+                        // `src`; lanes that take no clone have src == lane, so what they read back is their own state
+                        // and the assignments below need no select.
+                        p.P = __shfl_sync(kFull, p.P, src);
 #pragma unroll
-                        for (int k = 0; k < BW; ++k) b2[k] = __shfl_sync(kFull, p.bw[k], src);
-                        const double m2 = __shfl_sync(kFull, m1, src);
+                        for (int k = 0; k < BW; ++k) p.bw[k] = __shfl_sync(kFull, p.bw[k], src);
+                        const double m2 = __shfl_sync(kFull, m1, src);        // child 1 of src
                         const uint32_t r2 = __shfl_sync(kFull, rank1, src);
-                        float a2 = a, bb2 = b;
-                        if (!odd) { a2 = __shfl_sync(kFull, a, src); bb2 = __shfl_sync(kFull, b, src); }
-                        if (take) {
-                            p.P = P2;
-#pragma unroll
-                            for (int k = 0; k < BW; ++k) p.bw[k] = b2[k];
-                            p.m = m2; p.r = r2; bit = 1; p.alive = true;
-                            a = a2; b = bb2;
-                        } else if (s0) { p.m = m0; p.r = rank0; bit = 0; }
-                        else if (s1) { p.m = m1; p.r = rank1; bit = 1; }
-                        else p.alive = false;
+                        if (!odd) { a = __shfl_sync(kFull, a, src); b = __shfl_sync(kFull, b, src); }
+                        p.m = s0 ? m0 : m2;                                   // keep child 0 if it survives, else child 1 (own or cloned)
+                        p.r = s0 ? rank0 : r2;
+                        bit = s0 ? 0u : 1u;
+                        p.alive = s0 || s1 || take;
                     }
                 }
             }
-            if (p.alive) {
-                if (!odd) p.bw[0] = (p.bw[0] & ~1u) | bit;       // height-0 left buffer
-                else set_bit_odd(code, p, phi, bit);
-            }
+            if (!odd) p.bw[0] = (p.bw[0] & ~1u) | bit;           // height-0 left buffer
+            else set_bit_odd(code, p, phi, bit);
             if constexpr (MP > 1) __syncwarp();
         }
         // final list order = metric order (scl.py:173-174,183-188), ties by the last computed rank
@@ -295,17 +292,13 @@ struct ListDecoder {
                 for (int k = 0; k < XW; ++k) if (k == (phi >> 5)) cur_u = u[k];
             }
             const bool odd = phi & 1;
-            float L = 0.f;
-            if (active) {
-                if (!odd) { pair_llr(code, wm, q, phi, lane, chanf, a, b); L = f_op(a, b); }
-                else L = g_op(a, b, q.bw[0] & 1u);
-            }
+            float L;
+            if (!odd) { pair_llr(code, wm, q, phi, lane, chanf, a, b); L = f_op(a, b); }
+            else L = g_op(a, b, q.bw[0] & 1u);
             if ((cur_info >> (phi & 31)) & 1u) { if (active) sink(j, L); ++j; }
             const uint32_t bit = (cur_u >> (phi & 31)) & 1u;
-            if (active) {
-                if (!odd) q.bw[0] = (q.bw[0] & ~1u) | bit;
-                else set_bit_odd(code, q, phi, bit);
-            }
+            if (!odd) q.bw[0] = (q.bw[0] & ~1u) | bit;
+            else set_bit_odd(code, q, phi, bit);
         }
     }
 };
