@@ -93,10 +93,13 @@ __device__ __forceinline__ float softplus_tail(float L) {
 #else
 #define PB_LB
 #endif
-// Heights >= HS live in the global scratch.  HS = 6 keeps height 5 in shared memory (fewer L2 round trips) and
-// is best when registers, not shared memory, bound the occupancy (list kernels); HS = 5 maximises resident warps
-// (SC / M = 1 kernels, and the DL-SCL round kernels, which also hold the |L0| rows in shared memory).
-template <int MP> struct DefaultHS { static constexpr int value = (MP == 1) ? 5 : 6; };
+// Heights >= HS live in the global scratch.  HS = 5 (heights 5.. global, 30 rows = 3.8 KB of shared memory per warp)
+// lets the register count (64), not shared memory, set the occupancy: 32 warps per SM.  Because the tall levels are
+// evaluated depth-first (Tree::produce) the global rows are written once and read once per use.
+#ifndef PB_DEFAULT_HS
+#define PB_DEFAULT_HS 5
+#endif
+template <int MP> struct DefaultHS { static constexpr int value = PB_DEFAULT_HS; };
 
 __host__ __device__ inline int tree_rows_shared(int N, int hs) {
     const int all = N >= 6 ? N - 2 : 4;                 // rows of heights 1..n-1 (at least 4 rows of scratch)
@@ -272,9 +275,25 @@ struct Tree {
         }
     }
 
-    // Produce height H (>= 1) from height H+1 held at src[i*32] (tree, slot lane already folded into src) with
-    // OP 0 = f, 1 = g using the left bits of height H; store it in the own slot; continue with f down to the pair.
-    template <int H, int OP>
+    // bit e of the left-child buffer of height H (H in 4..6), for e = g + G*k with runtime g < G = 2^H/8 and
+    // static k: the word index depends on k only, so every register index stays static.
+    template <int H, int K>
+    static __device__ __forceinline__ uint32_t strided_bit(const uint32_t (&bw)[BW], int g) {
+        constexpr int G = (1 << H) / 8;
+        if constexpr (H == 4) return (bw[0] >> (15 + g + G * K)) & 1u;
+        else if constexpr (H == 5) return (bw[1] >> (g + G * K)) & 1u;
+        else return (bw[2 + (K >= 4 ? 1 : 0)] >> (g + G * (K & 3))) & 1u;     // H == 6: e < 32 iff K < 4
+    }
+
+    // Produce height H (>= 1) from height H+1 held at src[i*STRIDE] (STRIDE 32: a tree slot, lane folded into src;
+    // STRIDE 1: the channel row) with OP 0 = f, 1 = g using the left bits of height H; store it in the own slot and
+    // continue with f down to the height-1 pair.
+    //   H <= 3 : everything in registers.
+    //   H 4..6 : depth-first in groups of 8 strided elements {g + G*k}: they reduce in registers to 4 values of
+    //            height H-1, 2 of H-2 and 1 of H-3, so each level is stored once and never re-loaded (the tall rows
+    //            live in the L2-resident scratch; re-reading them was the dominant stall).
+    //   H >= 7 : (N >= 256) plain level loop, then recurse.
+    template <int H, int OP, int STRIDE>
     static __device__ __forceinline__ void produce(const float* src, const uint32_t (&bw)[BW], const WM& wm, int lane,
                                                    float& a, float& b) {
         constexpr int S = 1 << H;
@@ -283,40 +302,65 @@ struct Tree {
             float v[S];
 #pragma unroll
             for (int i = 0; i < S; ++i) {
-                const float x = src[i * 32], y = src[(i + S) * 32];
+                const float x = src[i * STRIDE], y = src[(i + S) * STRIDE];
                 v[i] = OP ? g_op(x, y, left_bit<H, BW>(bw, i)) : f_op(x, y);
                 if constexpr (H >= 2) own[((S - 2) + i) * 32] = v[i];
             }
             reg_chain<H>(v, wm, lane, a, b);
+        } else if constexpr (H <= 6) {
+            constexpr int G = S / 8;
+            float* o0 = own + (S - 2) * 32;
+            float* o1 = base<H - 1>(wm) + lane + (S / 2 - 2) * 32;
+            float* o2 = base<H - 2>(wm) + lane + (S / 4 - 2) * 32;
+            float* o3 = base<H - 3>(wm) + lane + (S / 8 - 2) * 32;
+            float r0 = 0.f, r1 = 0.f;
+#pragma unroll 1
+            for (int g = 0; g < G; ++g) {
+                float x[8], y[8], v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { x[k] = src[(g + G * k) * STRIDE]; y[k] = src[(g + G * k + S) * STRIDE]; }
+                v[0] = OP ? g_op(x[0], y[0], strided_bit<H, 0>(bw, g)) : f_op(x[0], y[0]);
+                v[1] = OP ? g_op(x[1], y[1], strided_bit<H, 1>(bw, g)) : f_op(x[1], y[1]);
+                v[2] = OP ? g_op(x[2], y[2], strided_bit<H, 2>(bw, g)) : f_op(x[2], y[2]);
+                v[3] = OP ? g_op(x[3], y[3], strided_bit<H, 3>(bw, g)) : f_op(x[3], y[3]);
+                v[4] = OP ? g_op(x[4], y[4], strided_bit<H, 4>(bw, g)) : f_op(x[4], y[4]);
+                v[5] = OP ? g_op(x[5], y[5], strided_bit<H, 5>(bw, g)) : f_op(x[5], y[5]);
+                v[6] = OP ? g_op(x[6], y[6], strided_bit<H, 6>(bw, g)) : f_op(x[6], y[6]);
+                v[7] = OP ? g_op(x[7], y[7], strided_bit<H, 7>(bw, g)) : f_op(x[7], y[7]);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o0[(g + G * k) * 32] = v[k];
+                float w[4], z[2];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { w[k] = f_op(v[k], v[k + 4]); o1[(g + G * k) * 32] = w[k]; }
+#pragma unroll
+                for (int k = 0; k < 2; ++k) { z[k] = f_op(w[k], w[k + 2]); o2[(g + G * k) * 32] = z[k]; }
+                const float r = f_op(z[0], z[1]);
+                if constexpr (H - 3 >= 2) o3[g * 32] = r;
+                else { if (g == 0) r0 = r; else r1 = r; }
+            }
+            if constexpr (H - 3 >= 2) chain_from<H - 3>(bw, wm, lane, a, b);
+            else { a = r0; b = r1; }
         } else {
             float* dst = own + (S - 2) * 32;
-            if constexpr (OP == 0) {
-#pragma unroll 8
-                for (int i = 0; i < S; ++i) dst[i * 32] = f_op(src[i * 32], src[(i + S) * 32]);
-            } else if constexpr (H == 4) {
-                const uint32_t bits = bw[0] >> 15;
-#pragma unroll 8
-                for (int i = 0; i < S; ++i) dst[i * 32] = g_op(src[i * 32], src[(i + S) * 32], (bits >> i) & 1u);
-            } else {
-                constexpr int W0 = (H == 5) ? 1 : (H == 6) ? 2 : (H == 7) ? 4 : 8;  // first word of height H
+            constexpr int W0 = (H == 7) ? 4 : 8;  // first word of height H
 #pragma unroll
-                for (int w = 0; w < S / 32; ++w) {
-                    const uint32_t bits = bw[(W0 + w) < BW ? (W0 + w) : 0];
+            for (int w = 0; w < S / 32; ++w) {
+                const uint32_t bits = OP ? bw[(W0 + w) < BW ? (W0 + w) : 0] : 0u;
 #pragma unroll 8
-                    for (int j = 0; j < 32; ++j) {
-                        const int i = w * 32 + j;
-                        dst[i * 32] = g_op(src[i * 32], src[(i + S) * 32], (bits >> j) & 1u);
-                    }
+                for (int j = 0; j < 32; ++j) {
+                    const int i = w * 32 + j;
+                    const float x = src[i * STRIDE], y = src[(i + S) * STRIDE];
+                    dst[i * 32] = OP ? g_op(x, y, (bits >> j) & 1u) : f_op(x, y);
                 }
             }
-            produce<H - 1, 0>(dst, bw, wm, lane, a, b);
+            produce<H - 1, 0, 32>(dst, bw, wm, lane, a, b);
         }
     }
 
     // f-chain from the own slot's height H (>= 2) down to the pair
     template <int H>
     static __device__ __forceinline__ void chain_from(const uint32_t (&bw)[BW], const WM& wm, int lane, float& a, float& b) {
-        produce<H - 1, 0>(base<H>(wm) + lane + (((1 << H) - 2) * 32), bw, wm, lane, a, b);
+        produce<H - 1, 0, 32>(base<H>(wm) + lane + (((1 << H) - 2) * 32), bw, wm, lane, a, b);
     }
 };
 

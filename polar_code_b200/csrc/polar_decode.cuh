@@ -15,61 +15,6 @@ struct ListDecoder {
     static constexpr int FPW = 32 / MP;
     static constexpr uint32_t GM = (MP >= 32) ? 0xffffffffu : ((1u << MP) - 1u);
 
-    static constexpr int TW = ((1 << LOGMAX) / 64) > 0 ? ((1 << LOGMAX) / 64) : 1;   // words of the tallest left buffer
-
-    // left-child bit buffer of (runtime, warp-uniform) height h as words tw[0..]; every register index is static
-    static __device__ __forceinline__ void height_words(const uint32_t (&bw)[BW], int h, uint32_t (&tw)[TW]) {
-#pragma unroll
-        for (int k = 0; k < TW; ++k) tw[k] = 0;
-        switch (h) {
-            case 5: tw[0] = bw[1]; break;
-            case 6: if constexpr (TW >= 2) { tw[0] = bw[2]; tw[1] = bw[3]; } break;
-            case 7: if constexpr (TW >= 4 && BW >= 8) { tw[0] = bw[4]; tw[1] = bw[5]; tw[2] = bw[6]; tw[3] = bw[7]; } break;
-            case 8: if constexpr (TW >= 8 && BW >= 16) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) tw[k] = bw[8 + k];
-            } break;
-            default: tw[0] = bw[0] >> ((1 << (h & 7)) - 1); break;   // h < 5: field of word 0
-        }
-    }
-
-    // height n-1 from the channel row: f at phi = 0, g (left bits of height n-1) at phi = N/2.  Runtime-sized loop;
-    // `chanf` may point into the caller's LLR buffer (global) or into the staged row.
-    static __device__ __forceinline__ void top_level(const Code& code, const WM& wm, const PathT& p, bool is_g, int lane,
-                                                     const float* chanf, float& a, float& b) {
-        const int half = code.N >> 1, h = code.n - 1;
-        if (half == 2) {  // N = 4: height 1 is the pair itself
-            const float v0 = is_g ? g_op(chanf[0], chanf[2], (p.bw[0] >> 1) & 1u) : f_op(chanf[0], chanf[2]);
-            const float v1 = is_g ? g_op(chanf[1], chanf[3], (p.bw[0] >> 2) & 1u) : f_op(chanf[1], chanf[3]);
-            a = v0; b = v1;
-            return;
-        }
-        float* dst = ((h >= HS) ? wm.tg : wm.ts) + lane + (half - 2) * 32;
-        const int nw = half >= 32 ? half / 32 : 1, per = half >= 32 ? 32 : half;
-        if (!is_g) {
-            for (int i = 0; i < half; i += 8) {
-                float v[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = (i + k < half) ? f_op(chanf[i + k], chanf[i + k + half]) : 0.f;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) if (i + k < half) dst[(i + k) * 32] = v[k];
-            }
-        } else {
-            uint32_t tw[TW];
-            height_words(p.bw, h, tw);
-#pragma unroll
-            for (int w = 0; w < TW; ++w) {
-                if (w < nw) {
-                    const uint32_t bits = tw[w];
-                    const float* x = chanf + w * 32;
-                    float* d = dst + w * 32 * 32;
-#pragma unroll 8
-                    for (int j = 0; j < per; ++j) d[j * 32] = g_op(x[j], x[j + half], (bits >> j) & 1u);
-                }
-            }
-        }
-    }
-
     // height-1 pair (a, b) of this lane's path for the EVEN phase `phi` (lazy form of scl.py:64-82)
     static __device__ __forceinline__ void pair_llr(const Code& code, const WM& wm, PathT& p, int phi, int lane,
                                                     const float* chanf, float& a, float& b) {
@@ -78,18 +23,27 @@ struct ListDecoder {
         if (n == 1) { a = chanf[0]; b = chanf[1]; return; }      // N = 2: the channel row is the pair
         const int c = (phi == 0) ? n - 1 : __ffs(phi) - 1;       // first height produced (>= 1)
         if (c == n - 1) {
-            top_level(code, wm, p, phi != 0, lane, chanf, a, b);
-            switch (c) {
-#define PB_CASE(HH) case HH: if constexpr (HH < LOGMAX) TreeT::template chain_from<HH>(p.bw, wm, lane, a, b); break;
-                PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7) PB_CASE(8)
+            // height n-1 straight from the channel row (stride 1): f at phi = 0, g at phi = N/2
+            if (phi == 0) {
+                switch (c) {
+#define PB_CASE(HH) case HH: if constexpr (HH < LOGMAX) TreeT::template produce<HH, 0, 1>(chanf, p.bw, wm, lane, a, b); break;
+                    PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7) PB_CASE(8)
 #undef PB_CASE
-                default: break;   // c == 1: top_level returned the pair
+                    default: break;
+                }
+            } else {
+                switch (c) {
+#define PB_CASE(HH) case HH: if constexpr (HH < LOGMAX) TreeT::template produce<HH, 1, 1>(chanf, p.bw, wm, lane, a, b); break;
+                    PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7) PB_CASE(8)
+#undef PB_CASE
+                    default: break;
+                }
             }
         } else {
             const uint32_t q = (p.P >> (4 * c)) & 0xfu;          // slot holding height c+1 (field c)
             const float* src = ((c + 1 >= HS) ? wm.tg : wm.ts) + (((2 << c) - 2) * 32) + gbase + q;
             switch (c) {
-#define PB_CASE(CC) case CC: if constexpr (CC + 1 < LOGMAX) TreeT::template produce<CC, 1>(src, p.bw, wm, lane, a, b); break;
+#define PB_CASE(CC) case CC: if constexpr (CC + 1 < LOGMAX) TreeT::template produce<CC, 1, 32>(src, p.bw, wm, lane, a, b); break;
                 PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7)
 #undef PB_CASE
                 default: break;
