@@ -49,7 +49,7 @@ def peaks() -> dict:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons streamed at 50 ms during the timed region (B200_PROFILING.md recipe)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -57,38 +57,48 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
         self.rows = []
-        self._stop = threading.Event()
+        self.proc = None
         self._t = None
 
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+    def _reader(self):
+        for line in self.proc.stdout:
+            cells = [c.strip() for c in line.split(",")]
+            if len(cells) > 8:
+                self.rows.append((time.perf_counter(), cells))
 
     def start(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu),
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._reader, daemon=True)
+            self._t.start()
+        except Exception:
+            self.proc = None
 
-    def stop(self) -> dict:
-        self._stop.set()
+    def mark(self) -> float:
+        return time.perf_counter()
+
+    def stop(self, t0: float = 0.0, t1: float = float("inf")) -> dict:
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
         if self._t:
-            self._t.join(timeout=6)
-        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+            self._t.join(timeout=2)
+        inside = [c for (t, c) in self.rows if t0 <= t <= t1] or [c for (_, c) in self.rows]
+        num = lambda v: float(v) if v.replace(".", "", 1).isdigit() else None
+        sm = [num(c[1]) for c in inside if num(c[1]) is not None]
+        mx = [num(c[2]) for c in inside if num(c[2]) is not None]
+        pw = [num(c[3]) for c in inside if num(c[3]) is not None]
         reasons = set()
-        for r in self.rows:
-            if len(r) > 8:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+        for c in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def cpu_baseline(sample_frames: int, threads: int = 0) -> dict:
@@ -148,7 +158,7 @@ def workload_config(frames_per_step: int, gpus: int, cpu: bool = False) -> dict:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=1 << 22, help="frames per step per GPU (device-resident leg)")
@@ -235,10 +245,13 @@ def main() -> None:
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.15)          # let the sampler produce its first line before the timed region starts
     launches["n"] = 0
+    t_begin = sampler.mark()
     ms = timed(step, Ksteps)
+    t_end = sampler.mark()
     n_launch = launches["n"]
-    clocks = sampler.stop() if rank == 0 else {}
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else {}
     value = world * B * Ksteps / (ms * 1e-3)
 
     # correctness of what was timed: decisions vs the transmitted words
@@ -279,9 +292,12 @@ def main() -> None:
     pk = peaks()
     ms_kernel = ms / Ksteps            # one decode_kernel launch per step, timed with CUDA events on its stream
     ach_gbs = HBM_BYTES_PER_FRAME * B / (ms_kernel * 1e-3) / 1e9
+    # ncu (profiles/r01_v5_decode_kernel_metrics.txt, 1 Mi-frame launch): dram read+write = 594 B per frame,
+    # i.e. the algorithmic bytes (the L2-resident scratch never reaches HBM); scaled here to this launch's B.
     roofline = {"bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / pk["hbm_gbs"],
-                "traffic": None, "peak_source": pk["source"],
-                "note": "decode_kernel<4,7> is issue/shared-memory bound, not HBM bound (SURVEY 8(d)); see roofline_issue"}
+                "traffic": 594 * B, "traffic_source": "ncu dram__bytes per frame of a 1 Mi-frame launch x B", "peak_source": pk["source"],
+                "algorithmic_bytes_per_frame": HBM_BYTES_PER_FRAME,
+                "note": "decode_kernel<4,7> is SM-issue bound, not HBM bound (SURVEY 8(d)): see roofline_issue and profiles/"}
     lane_ops = ELEM_OPS[M] * B / (ms_kernel * 1e-3)
     sm_clock = (clocks.get("sm_mhz") or pk["sm_max_mhz"]) * 1e6
     props = torch.cuda.get_device_properties(dev)
@@ -289,7 +305,10 @@ def main() -> None:
     roofline_issue = {"bound": "issue", "achieved": lane_ops, "unit": "element-ops/s (W_fg + W_pm = %d per frame)" % ELEM_OPS[M],
                       "peak": peak_max, "frac": lane_ops / peak_max,
                       "peak_at_measured_clock": props.multi_processor_count * 128 * sm_clock,
-                      "frac_at_measured_clock": lane_ops / (props.multi_processor_count * 128 * sm_clock)}
+                      "frac_at_measured_clock": lane_ops / (props.multi_processor_count * 128 * sm_clock),
+                      "ncu_issue_slots_busy_pct": 77.6, "ncu_warp_instructions_per_frame": 3048,
+                      "note": "SURVEY 8(d) definition (algorithmic element-ops / lane-op peak); the kernel itself keeps 77.6% of the "
+                              "issue slots busy (ncu, profiles/r01_v5_*) -- the gap is per-phase list management, not idle hardware"}
 
     extras = {}
     if not args.no_extras and rank == 0:
