@@ -129,6 +129,8 @@ struct pb200_engine {
     size_t q_bytes = 0;
     unsigned int* d_q_counts = nullptr;
     int q_counts_n = 0;
+    float* d_llr_store = nullptr;         // channel rows of frames in the DL-SCL retry queue (sweep mode)
+    size_t llr_store_bytes = 0;
     unsigned char* d_scratch = nullptr;   // per-warp global scratch of the decode kernels
     size_t scratch_bytes = 0;
 };
@@ -247,7 +249,7 @@ extern "C" void pb200_destroy(pb200_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaFree(e->d_info_pos); cudaFree(e->d_info_mask); cudaFree(e->d_crc_tab); cudaFree(e->d_rm_src); cudaFree(e->d_tx_src); cudaFree(e->d_enc_tab);
-    cudaFree(e->d_scratch); cudaFree(e->d_rm_dst); cudaFree(e->d_q[0]); cudaFree(e->d_q[1]); cudaFree(e->d_q_counts);
+    cudaFree(e->d_llr_store); cudaFree(e->d_scratch); cudaFree(e->d_rm_dst); cudaFree(e->d_q[0]); cudaFree(e->d_q[1]); cudaFree(e->d_q_counts);
     for (int i = 0; i < 3; ++i) {
         if (e->hs[i]) cudaStreamDestroy(e->hs[i]);
         cudaFree(e->d_stage_llr[i]); cudaFree(e->d_stage_bits[i]); cudaFree(e->d_stage_ok[i]); cudaFree(e->d_stage_flags[i]);

@@ -12,8 +12,15 @@ int sweep_build_tables(pb200_engine* e) {
 
 static size_t entry_bytes(const pb200_engine* e) { return e->code.n <= 7 ? sizeof(DlEntry<4>) : sizeof(DlEntry<16>); }
 
-static int ensure_queues(pb200_engine* e, long long frames, int retries) {
+static int ensure_queues(pb200_engine* e, long long frames, int retries, bool want_store) {
     const size_t need = (size_t)frames * entry_bytes(e);
+    const size_t need_store = want_store ? (size_t)frames * e->code.N * sizeof(float) : 0;
+    if (e->llr_store_bytes < need_store) {
+        cudaFree(e->d_llr_store);
+        e->d_llr_store = nullptr; e->llr_store_bytes = 0;
+        CUDA_TRY(cudaMalloc((void**)&e->d_llr_store, need_store));
+        e->llr_store_bytes = need_store;
+    }
     if (e->q_bytes < need) {
         cudaFree(e->d_q[0]); cudaFree(e->d_q[1]);
         e->d_q[0] = e->d_q[1] = nullptr; e->q_bytes = 0;
@@ -75,6 +82,8 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
     int rc = choose_cfg(e, base, MP, 4, warp_bytes(MP, code.N, 0), &kb);
     if (rc) return rc;
     const int fpw = 32 / MP;
+    // pieces of 4 Mi frames: with retries every queued frame keeps its LLR row (N floats) in the store, so the
+    // worst case (every frame fails) is 4 Mi x N x 4 B = 2 GB for N = 128 -- allocated lazily, grown on demand
     const long long piece_max = 1ll << 22;
     const long long total = a.n_frames, begin0 = a.frame_begin;
     const long long out_base = a.frame_begin;   // per-frame outputs are indexed by frame - frame_begin of the whole call
@@ -95,15 +104,16 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
         if (p.tried) p.tried += (size_t)off * p.R;
         if (p.flags) p.flags += off;
         if (a.retries > 0) {
-            rc = ensure_queues(e, nf, a.retries);
+            rc = ensure_queues(e, nf, a.retries, a.llr == nullptr);
             if (rc) return rc;
+            p.llr_store = (a.llr == nullptr) ? e->d_llr_store : nullptr;
             CUDA_TRY(cudaMemsetAsync(e->d_q_counts, 0, sizeof(unsigned int) * (a.retries + 2), st));
             p.q_capacity = (unsigned int)nf;
             p.q_out = e->d_q[0];
             p.q_out_count = e->d_q_counts;
         } else {
             // retries <= 0: nothing is ever enqueued, but the kernel still takes a valid counter
-            rc = ensure_queues(e, 1, 0);
+            rc = ensure_queues(e, 1, 0, false);
             if (rc) return rc;
             CUDA_TRY(cudaMemsetAsync(e->d_q_counts, 0, sizeof(unsigned int) * 2, st));
             p.q_capacity = 1;

@@ -83,10 +83,13 @@ struct SweepArgs {
     unsigned int* q_in_count;
     unsigned int* q_out_count;
     unsigned int q_capacity;
+    float* llr_store;              // [q_capacity][N] channel rows of the frames that entered the retry queue (Philox mode)
     unsigned char* gscratch;       // per-warp global scratch (WarpMem::gbytes each)
 };
 
-template <int XW> struct DlEntry { DlEntryHdr h; uint32_t u[XW]; uint32_t tried[XW]; };
+// retry-queue entry: best u-hat of the latest attempt, tried set (by info index), the transmitted word (for the
+// counters) and the row of the LLR store that holds this frame's channel LLRs (written once by the baseline pass)
+template <int XW> struct DlEntry { DlEntryHdr h; uint32_t u[XW]; uint32_t tried[XW]; uint32_t u_sent[XW]; uint32_t store; uint32_t pad; };
 
 // counters indices (include/polar_b200.h)
 enum { cFrames = 0, cSclFe, cSclBe, cDlFe, cDlBe, cUncFe, cUncBe, cDlWork, cNearTie, cSclUndet, cDlUndet, cRankTie, cNum };
@@ -358,21 +361,35 @@ struct Sweep {
         if (a.flags) a.flags[idx] = b.flags;
     }
 
-    // warp-aggregated append of the leaders with `need` to the output queue
-    static __device__ __forceinline__ void enqueue(const SweepArgs& a, int lane, bool need, long long frame, const Best& b,
-                                                   const uint32_t (&tried)[XW], uint32_t n_tried) {
+    // Warp-aggregated append of the leaders with `need` to the output queue.  `store` < 0: first time this frame is
+    // queued -> its channel row (chanf, N floats) is copied to llr_store[slot] and slot becomes its store index.
+    static __device__ __forceinline__ void enqueue(const Code& code, const SweepArgs& a, int lane, bool need, long long frame, const Best& b,
+                                                   const uint32_t (&tried)[XW], uint32_t n_tried, const uint32_t (&u_sent)[XW],
+                                                   long long store, const float* chanf) {
         const uint32_t m = __ballot_sync(kFull, need);
         if (m == 0) return;
         unsigned int base = 0;
         if (lane == 0) base = atomicAdd(a.q_out_count, (unsigned int)__popc(m));
         base = __shfl_sync(kFull, base, 0);
+        long long slot = -1;
         if (need) {
-            const unsigned int slot = base + __popc(m & ((1u << lane) - 1u));
-            if (slot < a.q_capacity) {
-                Entry* e = reinterpret_cast<Entry*>(a.q_out) + slot;
+            const unsigned int s = base + __popc(m & ((1u << lane) - 1u));
+            if (s < a.q_capacity) {
+                slot = s;
+                Entry* e = reinterpret_cast<Entry*>(a.q_out) + s;
                 e->h.frame = frame; e->h.flags = b.flags; e->h.n_tried = n_tried;
 #pragma unroll
-                for (int k = 0; k < XW; ++k) { e->u[k] = b.u[k]; e->tried[k] = tried[k]; }
+                for (int k = 0; k < XW; ++k) { e->u[k] = b.u[k]; e->tried[k] = tried[k]; e->u_sent[k] = u_sent[k]; }
+                e->store = (uint32_t)(store >= 0 ? store : s);
+                e->pad = 0;
+            }
+        }
+        if (a.llr_store != nullptr) {
+            // group lanes copy the row of a newly queued frame
+            const long long gslot = __shfl_sync(kFull, (store < 0) ? slot : -1ll, lane & ~(MP - 1));
+            if (gslot >= 0) {
+                float* dst = a.llr_store + gslot * (long long)code.N;
+                for (int i = lane & (MP - 1); i < code.N; i += MP) dst[i] = chanf[i];
             }
         }
     }
@@ -454,7 +471,7 @@ __global__ void __launch_bounds__(768) sweep_kernel(const Code code, const Table
         }
         if (a.retries >= 0) {
             if (leader && valid && !need) S::finish_dl(code, tb, a, wm, lane, my_frame, b, 0, u_sent, acc);
-            S::enqueue(a, lane, need, my_frame, b, tried, 0);
+            S::enqueue(code, a, lane, need, my_frame, b, tried, 0, u_sent, -1, chanf);
         }
         __syncwarp();
     }
@@ -486,31 +503,28 @@ __global__ void __launch_bounds__(640) dl_round_kernel(const Code code, const Ta
     for (long long g = (long long)blockIdx.x * wpc + warp; g < ngroups; g += (long long)gridDim.x * wpc) {
         const long long idx = g * FPW + fme;
         const bool valid = idx < (long long)n_in;
-        long long my_frame = -1;
+        long long my_frame = -1, store = 0;
         uint32_t eflags = 0, n_tried = 0;
-        uint32_t u_ref[XW], tried[XW];
+        uint32_t u_ref[XW], tried[XW], u_sent[XW];
 #pragma unroll
-        for (int k = 0; k < XW; ++k) { u_ref[k] = 0; tried[k] = 0; }
+        for (int k = 0; k < XW; ++k) { u_ref[k] = 0; tried[k] = 0; u_sent[k] = 0; }
         if (valid) {
             const Entry* e = reinterpret_cast<const Entry*>(a.q_in) + idx;
-            my_frame = e->h.frame; eflags = e->h.flags; n_tried = e->h.n_tried;
+            my_frame = e->h.frame; eflags = e->h.flags; n_tried = e->h.n_tried; store = e->store;
 #pragma unroll
-            for (int k = 0; k < XW; ++k) { u_ref[k] = e->u[k]; tried[k] = e->tried[k]; }
+            for (int k = 0; k < XW; ++k) { u_ref[k] = e->u[k]; tried[k] = e->tried[k]; u_sent[k] = e->u_sent[k]; }
         }
-        uint32_t u_sent[XW];
-        uint32_t unc = 0;
-        if (a.llr) {
-#pragma unroll
-            for (int k = 0; k < XW; ++k) u_sent[k] = 0;
+        // channel row of this frame: the caller's buffer (API mode), the LLR store (sweep mode), or -- with NR rate
+        // matching in API mode -- the de-rate-matched row staged by load_channel_ids
+        const float* chanf;
+        if (a.llr == nullptr) chanf = a.llr_store + store * (long long)code.N;
+        else if (tb.E == 0) chanf = a.llr + (valid ? (my_frame - a.frame_begin) : 0) * (long long)a.in_len;
+        else {
             load_channel_ids<MP, WM>(code, tb, wm, a.llr, a.in_len, my_frame, a.frame_begin, lane);
-        } else {
-            ChanCfg cc = a.cc;
-            cc.include_uncoded = 0;
-            gen_channel<MP, XW, WM>(code, tb, cc, wm, my_frame, lane, u_sent, unc, true);
+            chanf = wm.chan + fme * (code.N + 1);
         }
         // |L0| of the reference path (flip.py:102,133): replay it and keep the info-phase leaf LLRs
         float* ab = wm.absl + fme * (K + 1);
-        const float* chanf = wm.chan + fme * (code.N + 1);
         S::DecU::replay(code, tb.info_mask, wm, lane, valid, chanf, u_ref, [&](int j, float L) { if (leader) ab[j] = fabsf(L); });
         __syncwarp();
         // rank_indices (flip.py:104-108): first untried index of argsort(|L0| @ beta) = argmin over untried
@@ -584,7 +598,7 @@ __global__ void __launch_bounds__(640) dl_round_kernel(const Code code, const Ta
             need = !(pass || (int)n_tried >= a.retries || (int)n_tried >= K);   // flip.py:111,134
             if (!need) S::finish_dl(code, tb, a, wm, lane, my_frame, b, n_tried, u_sent, acc);
         }
-        S::enqueue(a, lane, need, my_frame, b, tried, n_tried);
+        S::enqueue(code, a, lane, need, my_frame, b, tried, n_tried, u_sent, store, chanf);
         __syncwarp();
     }
     S::flush(a, lane, acc);
