@@ -224,3 +224,59 @@ def test_fer_cli_end_to_end(tmp_path):
     assert lines[0] == "snr_db,fer_uncoded,ber_uncoded,fer_scl,ber_scl,fer_dl,ber_dl" and len(lines) == 2
     vals = [float(v) for v in lines[1].split(",")]
     assert vals[0] == 5.0 and 0.1 < vals[1] < 0.35 and vals[5] <= vals[3]     # uncoded FER ~0.22; DL-SCL never worse than SCL on CRC-FER
+
+
+def test_make_dataset_labels_match_oracle(tmp_path):
+    """batched dataset generation; labels / |L0| rows equal the frame-by-frame rule
+    (reference train/make_dataset.py:47-91) evaluated with the float64 oracle on the same LLRs."""
+    import json
+    import torch
+    from dl_scl_polar.train import make_dataset as D
+    from dl_scl_polar._engines import engine_for
+    from dl_scl_polar.polar.polar import construct_info_set
+    from polar_code_b200 import montecarlo as mc
+    A = construct_info_set(128, 64)
+    eng = engine_for(128, A, "0x1864CFB")
+    n, M = 20000, 2
+    msg, llr = eng.channel(noise_var=mc.fer_noise_var(4.0, 64, 128), n_frames=n, seed=5, stream_id=0, k_payload=40)
+    llr = llr * (1.0 - 2.0 * eng.encode(msg).to(torch.float32))
+    fail, abs_l0, label = D.label_failures(eng, llr, M, torch.zeros(64, dtype=torch.uint8, device=eng.dev))
+    fail, abs_l0, label = fail.cpu().numpy(), abs_l0.cpu().numpy(), label.cpu().numpy()
+    l64 = llr.cpu().numpy().astype(np.float64)
+    base = O.scl_decode_batch(l64, A, M, crc="0x1864CFB")
+    ofail = np.array([b for b in range(n) if not O.check_crc(base["best_bits"][b], "0x1864CFB")])
+    gaps_ok = base["min_gap"] > 1e-5
+    assert set(ofail[gaps_ok[ofail]]) <= set(fail) and len(fail) > 200
+    checked = 0
+    for row, b in enumerate(fail[:400]):
+        if not gaps_ok[b] or b not in set(ofail):
+            continue
+        ol0 = np.abs(base["info_llrs"][b, base["best_idx"][b]]).astype(np.float32)
+        np.testing.assert_allclose(abs_l0[row], ol0, rtol=1e-4, atol=2e-4)
+        srt = np.sort(ol0)
+        if np.min(np.diff(srt[:9])) < 1e-4:
+            continue                                        # |L0| order itself is a near tie
+        want = -1
+        for idx in np.argsort(ol0)[:8]:
+            force = np.full(64, -1, np.int8); force[:idx] = base["best_bits"][b][:idx]; force[idx] = 1 - base["best_bits"][b][idx]
+            r = O.scl_decode_batch(l64[b], A, M, crc="0x1864CFB", force=force)
+            if r["min_gap"][0] < 1e-5:
+                want = None
+                break
+            if O.check_crc(r["best_bits"][0], "0x1864CFB") and not r["best_bits"][0].any():
+                want = int(idx)
+                break
+        if want is not None:
+            assert label[row] == want, (b, label[row], want)
+            checked += 1
+    assert checked > 100
+    D.main(["--M", "2", "--snr_db", "4.0", "--frames", "30000", "--seed", "1", "--out", str(tmp_path / "train_M2")])
+    z = np.load(tmp_path / "train_M2_part0.npz")
+    meta = json.loads(str(z["meta"]))
+    assert z["abs_l0"].dtype == np.float32 and z["abs_l0"].shape[1] == 64 and z["flip_idx"].dtype == np.int32
+    assert z["abs_l0"].shape[0] == z["flip_idx"].shape[0] == meta["samples"] > 0
+    assert set(meta) == {"M", "EbN0_dB", "seed", "frames", "crc_poly", "crc_bits", "samples", "failures"}
+    assert ((z["flip_idx"] >= 0) & (z["flip_idx"] < 64)).all()
+    # the label is always among the 8 smallest |L0| positions of its row
+    rank = (z["abs_l0"] < z["abs_l0"][np.arange(len(z["flip_idx"])), z["flip_idx"]][:, None]).sum(axis=1)
+    assert (rank < 8).all()
