@@ -280,3 +280,22 @@ def test_make_dataset_labels_match_oracle(tmp_path):
     # the label is always among the 8 smallest |L0| positions of its row
     rank = (z["abs_l0"] < z["abs_l0"][np.arange(len(z["flip_idx"])), z["flip_idx"]][:, None]).sum(axis=1)
     assert (rank < 8).all()
+
+
+def test_dataset_train_sweep_loop(tmp_path):
+    """generate_samples -> train_beta -> run_sweep end to end (reference tests/test_cli_end2end.py:11-58)."""
+    from dl_scl_polar.train import make_dataset as D, train_beta as T
+    from dl_scl_polar.eval import run_fer_sweep as F
+    D.main(["--M", "2", "--snr_db", "4.0", "--frames", "40000", "--seed", "0", "--out", str(tmp_path / "data" / "train_M2")])
+    T.main(["--M", "2", "--data", str(tmp_path / "data" / "train_M2_part*.npz"), "--epochs", "2", "--batch", "256",
+            "--checkpoint_dir", str(tmp_path / "ck"), "--log_dir", str(tmp_path / "lg")])
+    beta = np.load(tmp_path / "ck" / "beta_M2.npy")
+    assert beta.shape == (64, 64) and np.allclose(beta, beta.T) and np.allclose(np.diag(beta), 1.0)
+    F.main(["--M", "2", "--frames", "20000", "--snr_lo", "4.0", "--snr_hi", "4.5", "--retries", "8", "--beta",
+            str(tmp_path / "ck" / "beta_M2.npy"), "--out_dir", str(tmp_path / "res"), "--plot_dir", str(tmp_path / "plt")])
+    lines = (tmp_path / "res" / "fer_M2.csv").read_text().splitlines()
+    assert lines[0] == "snr_db,fer_scl,ber_scl,fer_dl,ber_dl" and len(lines) == 3
+    for ln in lines[1:]:
+        v = [float(x) for x in ln.split(",")]
+        assert 0 < v[3] <= v[1] < 0.5                         # DL-SCL CRC-FER never above SCL's
+    assert (tmp_path / "plt" / "fer_M2.png").exists()
