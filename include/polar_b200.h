@@ -12,7 +12,9 @@
  *   - `d_` pointers are DEVICE pointers, `h_` pointers are HOST pointers; all buffers are caller-owned
  *   - every call returns 0 on success or a negative PB200_E* code; pb200_last_error() gives the text
  *   - calls only enqueue work on `stream` unless stated otherwise (the *_host calls synchronise)
- *   - a handle is not thread-safe; use one handle per GPU / rank
+ *   - a handle is not thread-safe; use one handle per GPU / rank.  Decode calls of one handle may be enqueued on
+ *     different streams (each stream gets its own scratch); pb200_sweep / pb200_dlscl_decode_batch share the
+ *     handle's retry queues and must be stream-ordered with respect to each other
  *   - there is NO CPU fallback: without a CUDA device pb200_create fails with PB200_ECUDA
  */
 #ifndef POLAR_B200_H
@@ -126,7 +128,8 @@ int pb200_scl_decode_host(pb200_engine *e, const float *h_llr, int64_t B, int in
  * counters (int64, ADDED to, so a rank can accumulate and then all-reduce the block):
  *   [0] frames            [1] scl_frame_errors   [2] scl_bit_errors   [3] dl_frame_errors
  *   [4] dl_bit_errors     [5] uncoded_frame_err  [6] uncoded_bit_err  [7] dl_attempts_minus_1 (sum)
- *   [8] near_tie_frames   [9] scl_undetected (CRC pass but wrong word)  [10..15] reserved
+ *   [8] near_tie_frames   [9] scl_undetected (CRC pass but wrong word)   [10] dl_undetected
+ *   [11] rank_tie_frames  [12..15] reserved
  */
 #define PB200_NCOUNTERS 16
 typedef struct {

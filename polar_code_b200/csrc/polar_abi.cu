@@ -131,8 +131,9 @@ struct pb200_engine {
     int q_counts_n = 0;
     float* d_llr_store = nullptr;         // channel rows of frames in the DL-SCL retry queue (sweep mode)
     size_t llr_store_bytes = 0;
-    unsigned char* d_scratch = nullptr;   // per-warp global scratch of the decode kernels
-    size_t scratch_bytes = 0;
+    // per-warp global scratch of the decode kernels, one buffer per stream: kernels of one engine that are
+    // enqueued on different streams may overlap on the device and must not share tree rows
+    std::map<cudaStream_t, std::pair<unsigned char*, size_t>> scratch;
 };
 int sweep_build_tables(pb200_engine* e);
 
@@ -249,7 +250,8 @@ extern "C" void pb200_destroy(pb200_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaFree(e->d_info_pos); cudaFree(e->d_info_mask); cudaFree(e->d_crc_tab); cudaFree(e->d_rm_src); cudaFree(e->d_tx_src); cudaFree(e->d_enc_tab);
-    cudaFree(e->d_llr_store); cudaFree(e->d_scratch); cudaFree(e->d_rm_dst); cudaFree(e->d_q[0]); cudaFree(e->d_q[1]); cudaFree(e->d_q_counts);
+    cudaFree(e->d_llr_store); cudaFree(e->d_rm_dst);
+    for (auto& kv : e->scratch) cudaFree(kv.second.first); cudaFree(e->d_q[0]); cudaFree(e->d_q[1]); cudaFree(e->d_q_counts);
     for (int i = 0; i < 3; ++i) {
         if (e->hs[i]) cudaStreamDestroy(e->hs[i]);
         cudaFree(e->d_stage_llr[i]); cudaFree(e->d_stage_bits[i]); cudaFree(e->d_stage_ok[i]); cudaFree(e->d_stage_flags[i]);
@@ -310,15 +312,20 @@ static size_t warp_gbytes(int MP, int N) {
     }
 }
 
-// global scratch for `warps` resident warps (grows on demand; stays L2-resident across launches)
-static int ensure_scratch(pb200_engine* e, size_t warps, int MP) {
+// global scratch for `warps` resident warps of a launch on `st` (grows on demand; stays L2-resident across launches)
+static int ensure_scratch(pb200_engine* e, cudaStream_t st, size_t warps, int MP, unsigned char** out) {
     const size_t need = warps * warp_gbytes(MP, e->code.N) + 256;
-    if (e->scratch_bytes < need) {
-        cudaFree(e->d_scratch);
-        e->d_scratch = nullptr; e->scratch_bytes = 0;
-        CUDA_TRY(cudaMalloc((void**)&e->d_scratch, need));
-        e->scratch_bytes = need;
+    auto& slot = e->scratch[st];
+    if (slot.second < need) {
+        if (slot.first) {
+            CUDA_TRY(cudaStreamSynchronize(st));     // earlier launches on this stream may still use the old buffer
+            cudaFree(slot.first);
+        }
+        slot.first = nullptr; slot.second = 0;
+        CUDA_TRY(cudaMalloc((void**)&slot.first, need));
+        slot.second = need;
     }
+    *out = slot.first;
     return PB200_OK;
 }
 
@@ -377,10 +384,9 @@ static int launch_decode(pb200_engine* e, int M, bool metric, const DecodeArgs& 
     const int64_t groups = (a.B + fpw - 1) / fpw;
     const int64_t want = (groups + kc.wpc - 1) / kc.wpc;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)e->sms * kc.ctas_per_sm));
-    rc = ensure_scratch(e, (size_t)grid * kc.wpc, MP);
-    if (rc) return rc;
     DecodeArgs aa = a;
-    aa.gscratch = e->d_scratch;
+    rc = ensure_scratch(e, st, (size_t)grid * kc.wpc, MP, &aa.gscratch);
+    if (rc) return rc;
     void* args[3] = {(void*)&code, (void*)&e->tb, (void*)&aa};
     CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(kc.wpc * 32), args, kc.smem, st));
     return PB200_OK;

@@ -123,9 +123,8 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
         const long long groups = (nf + fpw - 1) / fpw;
         const long long want = (groups + kb.wpc - 1) / kb.wpc;
         const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)e->sms * kb.ctas_per_sm));
-        rc = ensure_scratch(e, (size_t)grid * kb.wpc, MP);
+        rc = ensure_scratch(e, st, (size_t)grid * kb.wpc, MP, &p.gscratch);
         if (rc) return rc;
-        p.gscratch = e->d_scratch;
         {
             void* args[3] = {(void*)&code, (void*)&e->tb, (void*)&p};
             CUDA_TRY(cudaLaunchKernel(base, dim3(grid), dim3(kb.wpc * 32), args, kb.smem, st));
@@ -136,9 +135,8 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
             const long long rgroups = (nf + fpw - 1) / fpw;
             const long long rwant = (rgroups + kr.wpc - 1) / kr.wpc;
             const int rgrid = (int)std::max<long long>(1, std::min<long long>(rwant, (long long)e->sms * kr.ctas_per_sm));
-            rc = ensure_scratch(e, (size_t)std::max(rgrid * kr.wpc, grid * kb.wpc), MP);
+            rc = ensure_scratch(e, st, (size_t)std::max(rgrid * kr.wpc, grid * kb.wpc), MP, &p.gscratch);
             if (rc) return rc;
-            p.gscratch = e->d_scratch;
             for (int r = 0; r < a.retries; ++r) {
                 SweepArgs q = p;
                 q.q_in = e->d_q[r & 1];
@@ -214,9 +212,8 @@ extern "C" int pb200_channel_batch(pb200_engine* e, const pb200_sweep_cfg* c, ui
     const int wpc = 4;
     const long long groups = (c->n_frames + 7) / 8;
     const int grid = (int)std::max<long long>(1, std::min<long long>((groups + wpc - 1) / wpc, (long long)e->sms * 8));
-    rc = ensure_scratch(e, (size_t)grid * wpc, 4);
+    rc = ensure_scratch(e, (cudaStream_t)stream, (size_t)grid * wpc, 4, &a.gscratch);
     if (rc) return rc;
-    a.gscratch = e->d_scratch;
     {
         const void* fn = pb_channel_kernel(e->code.n);
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wb * wpc)));
