@@ -163,13 +163,6 @@ static unsigned long long xpow_mod(int e, unsigned long long poly, int deg) {
     return r;
 }
 
-static void host_transform(std::vector<uint8_t>& x) {  // polar.py:17-29
-    const int N = (int)x.size();
-    for (int step = 1; step < N; step <<= 1)
-        for (int start = 0; start < N; start += 2 * step)
-            for (int i = 0; i < step; ++i) x[start + i] ^= x[start + step + i];
-}
-
 extern "C" int pb200_create(pb200_engine** out, int device, int N, const int32_t* info_set, int K, const char* crc_poly) {
     if (!out) return fail(PB200_EINVAL, "out is NULL");
     *out = nullptr;

@@ -148,3 +148,51 @@ def test_nr_sweep_and_ber_point(eng):
     ee = err.cpu().numpy().astype(np.int64)
     frames = int(np.argmax(np.cumsum(ee) >= 50)) + 1
     assert (st.frames, st.bit_errors) == (frames, int(ee[:frames].sum()))
+
+
+def test_full_size_sweep_properties(eng):
+    """BASELINE configs[1] size: 1e7 frames at one SNR point.  Properties that do not need the oracle: the counters of
+    three unequal shards add up to the single-launch counters; frame errors <= frames; bit errors are consistent with
+    frame errors; SC (M=1) is never better than SCL M=4 in CRC-failure rate on the same frames."""
+    n = 10_000_000
+    kw = dict(noise_var=_nv(5.5), seed=123, stream_id=55, k_payload=40)
+    whole = _counters(eng, M=4, n_frames=n, **kw)
+    parts = sum(_counters(eng, M=4, n_frames=c, frame_begin=b, **kw) for b, c in [(0, 1), (1, 3_999_999), (4_000_000, 6_000_000)])
+    assert np.array_equal(whole, parts)
+    assert whole[0] == n and 0 < whole[1] < n and whole[2] >= whole[1] - whole[9]
+    sc = _counters(eng, M=1, n_frames=n, **kw)
+    assert sc[1] >= whole[1]
+    fer = whole[1] / n
+    assert 0.005 < fer < 0.03            # SCL M=4 at 5.5 dB (reference fer_M4-like operating point)
+
+
+def test_decode_calls_on_different_streams_do_not_interfere(eng):
+    """Two decode launches of ONE engine enqueued on two streams (they may overlap on the device) give the same
+    results as serial execution -- each stream owns its scratch."""
+    msg, llr = eng.channel(noise_var=_nv(4.0), n_frames=1 << 19, seed=3, stream_id=1, k_payload=40)
+    ref = eng.scl_decode(llr, 4, want=("best_bits", "crc_ok"))
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    half = llr.shape[0] // 2
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            a = eng.scl_decode(llr[:half], 4, want=("best_bits", "crc_ok"))
+        with torch.cuda.stream(s2):
+            b = eng.scl_decode(llr[half:], 4, want=("best_bits", "crc_ok"))
+        torch.cuda.synchronize()
+        assert torch.equal(a["best_bits"], ref["best_bits"][:half]) and torch.equal(b["best_bits"], ref["best_bits"][half:])
+
+
+def test_host_buffer_path_matches_device_path(eng):
+    """pb200_scl_decode_host (chunked, three internal streams) == device-resident decode, ragged batch size."""
+    n = (1 << 19) + 12345
+    msg, llr = eng.channel(noise_var=_nv(4.5), n_frames=n, seed=8, stream_id=2, k_payload=40)
+    ref = eng.scl_decode(llr, 4, want=("best_bits", "crc_ok", "flags"))
+    h_llr = torch.empty((n, 128), dtype=torch.float32, pin_memory=True)
+    h_llr.copy_(llr)
+    h_bits = torch.empty((n, 64), dtype=torch.uint8, pin_memory=True)
+    h_ok = torch.empty((n,), dtype=torch.uint8, pin_memory=True)
+    h_fl = torch.empty((n,), dtype=torch.int32, pin_memory=True)
+    eng.scl_decode_host(h_llr, 4, h_bits, h_ok, h_fl)
+    assert torch.equal(h_bits, ref["best_bits"].cpu()) and torch.equal(h_ok, ref["crc_ok"].cpu())
+    assert torch.equal(h_fl, ref["flags"].cpu())
