@@ -99,6 +99,9 @@ __device__ __forceinline__ float softplus_tail(float L) {
 #ifndef PB_DEFAULT_HS
 #define PB_DEFAULT_HS 5
 #endif
+// staged channel rows: [frame][chan_stride(N)] floats -- rows stay 16-byte aligned for vector loads
+__host__ __device__ inline int chan_stride(int N) { return N + 4; }
+
 template <int MP> struct DefaultHS { static constexpr int value = PB_DEFAULT_HS; };
 
 __host__ __device__ inline int tree_rows_shared(int N, int hs) {
@@ -130,7 +133,7 @@ struct WarpMem {
     }
     __host__ __device__ static size_t gbytes(int N) {                     // global scratch bytes per warp
         size_t t = (size_t)tree_rows_global(N, HS) * 32 * 4;
-        size_t ch = (((size_t)FPW * (N + 1) * 4) + 127) & ~(size_t)127;
+        size_t ch = (((size_t)FPW * chan_stride(N) * 4) + 127) & ~(size_t)127;
         return t + ch;
     }
     __device__ void carve(unsigned char* sbase, unsigned char* gbase, int N) {
@@ -314,11 +317,9 @@ struct Tree {
             float* o2 = base<H - 2>(wm) + lane + (S / 4 - 2) * 32;
             float* o3 = base<H - 3>(wm) + lane + (S / 8 - 2) * 32;
             float r0 = 0.f, r1 = 0.f;
-#pragma unroll 1
-            for (int g = 0; g < G; ++g) {
-                float x[8], y[8], v[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) { x[k] = src[(g + G * k) * STRIDE]; y[k] = src[(g + G * k + S) * STRIDE]; }
+            // one group = the 8 strided elements {g + G*k}: reduce them to heights H-1, H-2, H-3 in registers
+            auto group = [&](int g, const float (&x)[8], const float (&y)[8]) {
+                float v[8];
                 v[0] = OP ? g_op(x[0], y[0], strided_bit<H, 0>(bw, g)) : f_op(x[0], y[0]);
                 v[1] = OP ? g_op(x[1], y[1], strided_bit<H, 1>(bw, g)) : f_op(x[1], y[1]);
                 v[2] = OP ? g_op(x[2], y[2], strided_bit<H, 2>(bw, g)) : f_op(x[2], y[2]);
@@ -337,6 +338,30 @@ struct Tree {
                 const float r = f_op(z[0], z[1]);
                 if constexpr (H - 3 >= 2) o3[g * 32] = r;
                 else { if (g == 0) r0 = r; else r1 = r; }
+            };
+            if constexpr (STRIDE == 1 && G >= 2 && MP == 1) {
+                // channel row (each lane walks its own row, i.e. every request touches up to 32 lines): read it with
+                // 8-byte loads, two neighbouring groups per iteration, to halve the L1 tag look-ups
+#pragma unroll 1
+                for (int g = 0; g < G; g += 2) {
+                    float x0[8], y0[8], x1[8], y1[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float2 xa = *reinterpret_cast<const float2*>(src + g + G * k);
+                        const float2 ya = *reinterpret_cast<const float2*>(src + g + G * k + S);
+                        x0[k] = xa.x; x1[k] = xa.y; y0[k] = ya.x; y1[k] = ya.y;
+                    }
+                    group(g, x0, y0);
+                    group(g + 1, x1, y1);
+                }
+            } else {
+#pragma unroll 1
+                for (int g = 0; g < G; ++g) {
+                    float x[8], y[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { x[k] = src[(g + G * k) * STRIDE]; y[k] = src[(g + G * k + S) * STRIDE]; }
+                    group(g, x, y);
+                }
             }
             if constexpr (H - 3 >= 2) chain_from<H - 3>(bw, wm, lane, a, b);
             else { a = r0; b = r1; }

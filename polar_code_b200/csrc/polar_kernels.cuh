@@ -51,7 +51,7 @@ __device__ __forceinline__ void load_channel(const Code& code, const Tables& tb,
                 v = cnt ? acc / (float)cnt : -1.0f;
             }
         }
-        wm.chan[f * (N + 1) + i] = v;
+        wm.chan[f * chan_stride(N) + i] = v;
     }
     __syncwarp();
 }
@@ -137,7 +137,7 @@ __global__ void PB_LB decode_kernel(const Code code, const Tables tb, const Deco
         if (tb.E == 0) chanf = a.llr + (valid ? frame : 0) * (int64_t)a.in_len;      // rows are decoded in place
         else {
             load_channel<MP, WM>(code, tb, wm, a.llr, a.in_len, frame0, a.B, lane);
-            chanf = wm.chan + (lane / MP) * (code.N + 1);
+            chanf = wm.chan + (lane / MP) * chan_stride(code.N);
         }
         uint32_t flags = 0;
         uint32_t fmask[XW], fval[XW];

@@ -205,7 +205,7 @@ __device__ __forceinline__ void gen_channel(const Code& code, const Tables& tb, 
     const int Eeff = nr ? tb.E : N;
     const int nblk = N >= 4 ? N / 4 : 1;
     if (nr && !raw_out) {
-        for (int e = lane; e < FPW * N; e += 32) wm.chan[(e >> code.n) * (N + 1) + (e & (N - 1))] = 0.f;
+        for (int e = lane; e < FPW * N; e += 32) wm.chan[(e >> code.n) * chan_stride(N) + (e & (N - 1))] = 0.f;
         __syncwarp();
     }
     const int rounds = (Eeff + N - 1) / N;
@@ -226,10 +226,10 @@ __device__ __forceinline__ void gen_channel(const Code& code, const Tables& tb, 
                     if (src >= 0) s = 1.0f - 2.0f * (float)((scr[(R2 + (src >> 5)) * 32 + f * MP] >> (src & 31)) & 1u);
                     const float llr = fmaf(cc.sigma, z[c], s) * cc.scale;
                     if (raw_out) raw_out[(fr - raw_base) * (long long)Eeff + t] = llr;
-                    else if (!nr) wm.chan[f * (N + 1) + t] = llr;
+                    else if (!nr) wm.chan[f * chan_stride(N) + t] = llr;
                     else {
                         const int dst = __ldg(&cc.rm_dst[p]);
-                        if (dst >= 0) wm.chan[f * (N + 1) + dst] += llr;   // k ascending = the order of load_channel
+                        if (dst >= 0) wm.chan[f * chan_stride(N) + dst] += llr;   // k ascending = the order of load_channel
                     }
                 }
             }
@@ -243,9 +243,9 @@ __device__ __forceinline__ void gen_channel(const Code& code, const Tables& tb, 
             float v = 0.f;
             if (p >= 0) {
                 const int cnt = p < Eeff ? (Eeff - p + N - 1) / N : 0;
-                v = cnt ? wm.chan[f * (N + 1) + i] / (float)cnt : -1.0f;
+                v = cnt ? wm.chan[f * chan_stride(N) + i] / (float)cnt : -1.0f;
             }
-            wm.chan[f * (N + 1) + i] = v;
+            wm.chan[f * chan_stride(N) + i] = v;
         }
         __syncwarp();
     }
@@ -278,7 +278,7 @@ __device__ __forceinline__ void load_channel_ids(const Code& code, const Tables&
                 }
             }
         }
-        wm.chan[f * (N + 1) + i] = v;
+        wm.chan[f * chan_stride(N) + i] = v;
     }
     __syncwarp();
 }
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(768) sweep_kernel(const Code code, const Table
         uint32_t fm[XW], fv[XW];
         PathT p;
         S::DecU::init(p, lane, valid);
-        const float* chanf = wm.chan + (lane / MP) * (code.N + 1);
+        const float* chanf = wm.chan + (lane / MP) * chan_stride(code.N);
         S::DecU::run(code, tb.info_mask, wm, p, lane, chanf, fm, fv, flags);
         typename S::Best b;
         S::pick_best(code, tb, p, lane, flags, b);
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(640) dl_round_kernel(const Code code, const Ta
         else if (tb.E == 0) chanf = a.llr + (valid ? (my_frame - a.frame_begin) : 0) * (long long)a.in_len;
         else {
             load_channel_ids<MP, WM>(code, tb, wm, a.llr, a.in_len, my_frame, a.frame_begin, lane);
-            chanf = wm.chan + fme * (code.N + 1);
+            chanf = wm.chan + fme * chan_stride(code.N);
         }
         // |L0| of the reference path (flip.py:102,133): replay it and keep the info-phase leaf LLRs
         float* ab = wm.absl + fme * (K + 1);
