@@ -126,14 +126,17 @@ def cpu_baseline(sample_frames: int, threads: int = 0) -> dict:
 
 
 def run_reference(args) -> None:
+    """Reference arm: the CPU path (pinned C oracle, all host threads) on bounded samples of the same workload.
+    Under torchrun only rank 0 works; the other ranks exit 0."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warm = args.steps, args.warmup
-    sample = args.cpu_sample
-    for _ in range(max(warm, 1) - 1):
-        cpu_baseline(sample // 8)
-    vals = [cpu_baseline(sample) for _ in range(max(steps, 1))]
+    steps, warm = max(args.steps, 1), max(args.warmup, 0)
+    # keep the whole run within a few minutes whatever K is: ~2.4 M frames of CPU work in total (about 10 s on 16 cores)
+    sample = int(min(args.cpu_sample, max(60_000, 2_400_000 // steps)))
+    for _ in range(min(warm, 2)):
+        cpu_baseline(max(sample // 4, 12_000))
+    vals = [cpu_baseline(sample) for _ in range(steps)]
     v = float(np.mean([x["value"] for x in vals]))
     cb = dict(vals[-1])
     cb["value"] = v
