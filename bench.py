@@ -248,7 +248,9 @@ def main() -> None:
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.15)          # let the sampler produce its first line before the timed region starts
+        t_wait = time.perf_counter()
+        while not sampler.rows and time.perf_counter() - t_wait < 3.0:   # first nvidia-smi line before the timed region
+            time.sleep(0.02)
     launches["n"] = 0
     t_begin = sampler.mark()
     ms = timed(step, Ksteps)

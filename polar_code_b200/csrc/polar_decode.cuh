@@ -127,14 +127,15 @@ struct ListDecoder {
                 if (is_forced) bit = forced_val;
             } else {
                 const float tail = softplus_tail(L);
-                const double m0 = p.m + ((double)fmaxf(-L, 0.f) + (double)tail);   // bit 0: logaddexp(0,-L)
-                const double m1 = p.m + ((double)fmaxf(L, 0.f) + (double)tail);    // bit 1: logaddexp(0, L)
+                const double dtail = (double)tail;
+                const double m0 = p.m + ((double)fmaxf(-L, 0.f) + dtail);          // bit 0: logaddexp(0,-L)
                 bool a0 = p.alive, a1 = p.alive && is_info;
                 if (is_forced) {
                     a0 = a0 && (forced_val == 0);
                     a1 = a1 && (forced_val == 1);
                 }
                 if constexpr (MP == 1) {
+                    const double m1 = p.m + ((double)fmaxf(L, 0.f) + dtail);       // bit 1: logaddexp(0, L)
                     bool pick1 = a1 && (!a0 || m1 < m0);
                     if (a0 && a1) {
                         const uint32_t h0 = (uint32_t)(__double_as_longlong(m0) >> 32), h1 = (uint32_t)(__double_as_longlong(m1) >> 32);
@@ -152,12 +153,13 @@ struct ListDecoder {
                     } else {
                         // Keys: IEEE bits of the (non-negative) fp64 metric with the stable-sort tie-break 2*rank+bit in
                         // the 4 lowest mantissa bits.  They order identically as integers and as doubles, so the rank
-                        // compares run on the otherwise idle FP64 pipe (one DSETP each); a dead candidate is NaN.
-                        const unsigned long long dead = ~0ull;
+                        // compares run on the otherwise idle FP64 pipe (one DSETP each).  A dead candidate gets a huge
+                        // finite key that is unique in its group, so EVERY candidate has a unique rank (dead ones last).
+                        const double m1 = p.m + ((double)fmaxf(L, 0.f) + dtail);   // bit 1: logaddexp(0, L)
+                        const unsigned long long dead = 0x7fe0000000000000ull | (unsigned long long)(2 * slot);
                         const unsigned long long k0 = a0 ? (((unsigned long long)__double_as_longlong(m0) & ~15ull) | (2u * p.r)) : dead;
-                        const unsigned long long k1 = a1 ? (((unsigned long long)__double_as_longlong(m1) & ~15ull) | (2u * p.r + 1u)) : dead;
+                        const unsigned long long k1 = a1 ? (((unsigned long long)__double_as_longlong(m1) & ~15ull) | (2u * p.r + 1u)) : (dead | 1ull);
                         reinterpret_cast<ulonglong2*>(wm.xchg)[lane] = make_ulonglong2(k0, k1);
-                        *reinterpret_cast<uint2*>(hs + 2 * lane) = make_uint2(0xffffffffu, 0xffffffffu);
                         __syncwarp();
                         const double d0 = __longlong_as_double((long long)k0), d1 = __longlong_as_double((long long)k1);
                         uint32_t rank0 = 0, rank1 = 0;
@@ -171,8 +173,8 @@ struct ListDecoder {
                         const bool s0 = a0 && rank0 < M, s1 = a1 && rank1 < M;   // scl.py:174 keep the M best
                         // near-tie test on rank-sorted neighbours: a kept candidate and its successor within ~1e-6 relative
                         const uint32_t h0 = (uint32_t)(k0 >> 32), h1 = (uint32_t)(k1 >> 32);
-                        if (a0) hs[2 * gbase + rank0] = h0;
-                        if (a1) hs[2 * gbase + rank1] = h1;
+                        hs[2 * gbase + rank0] = h0;                               // all 2*MP ranks of the group are written
+                        hs[2 * gbase + rank1] = h1;
                         __syncwarp();
                         if (s0 && rank0 + 1 < 2 * MP && (uint32_t)(hs[2 * gbase + rank0 + 1] - h0) <= 2u) tie = 1;
                         if (s1 && rank1 + 1 < 2 * MP && (uint32_t)(hs[2 * gbase + rank1 + 1] - h1) <= 2u) tie = 1;
@@ -191,9 +193,24 @@ struct ListDecoder {
                         // The second child of a doubly-surviving path moves into a freed slot.  Every lane reads from
                         // `src`; lanes that take no clone have src == lane, so what they read back is their own state
                         // and the assignments below need no select.
+                        // (a left buffer of height h is live only while bit h of phi is set: words of dead heights
+                        //  are rewritten before their next use and need not travel)
                         p.P = __shfl_sync(kFull, p.P, src);
+                        p.bw[0] = __shfl_sync(kFull, p.bw[0], src);
+                        if (phi & 32) p.bw[1] = __shfl_sync(kFull, p.bw[1], src);
+                        if (phi & 64) { p.bw[2] = __shfl_sync(kFull, p.bw[2], src); p.bw[3] = __shfl_sync(kFull, p.bw[3], src); }
+                        if constexpr (BW >= 8) {
+                            if (phi & 128) {
 #pragma unroll
-                        for (int k = 0; k < BW; ++k) p.bw[k] = __shfl_sync(kFull, p.bw[k], src);
+                                for (int k = 4; k < 8; ++k) p.bw[k] = __shfl_sync(kFull, p.bw[k], src);
+                            }
+                        }
+                        if constexpr (BW >= 16) {
+                            if (phi & 256) {
+#pragma unroll
+                                for (int k = 8; k < 16; ++k) p.bw[k] = __shfl_sync(kFull, p.bw[k], src);
+                            }
+                        }
                         const double m2 = __shfl_sync(kFull, m1, src);        // child 1 of src
                         const uint32_t r2 = __shfl_sync(kFull, rank1, src);
                         if (!odd) { a = __shfl_sync(kFull, a, src); b = __shfl_sync(kFull, b, src); }

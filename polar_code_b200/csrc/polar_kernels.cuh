@@ -72,11 +72,12 @@ __device__ __forceinline__ uint32_t crc_syndrome(const Code& code, const Tables&
     return syn;
 }
 
-// Write the K information bits of the word stashed at stash[w*32] (w = phase/32) as bytes.
-__device__ __forceinline__ void write_info_bits(const Code& code, const Tables& tb, const float* stash, uint8_t* dst) {
-    const int K = code.K;
-    const bool al = ((reinterpret_cast<uintptr_t>(dst) & 3) == 0);
-    int j = 0;
+// Write information bits [j0, j1) of the word stashed at stash[w*32] (w = phase/32) as bytes dst[j].
+__device__ __forceinline__ void write_info_bits(const Code& code, const Tables& tb, const float* stash, uint8_t* dst,
+                                                int j0 = 0, int j1 = -1) {
+    const int K = (j1 < 0) ? code.K : j1;
+    const bool al = ((reinterpret_cast<uintptr_t>(dst + j0) & 3) == 0);
+    int j = j0;
     for (; j + 4 <= K && al; j += 4) {
         uint32_t w = 0;
 #pragma unroll
@@ -172,11 +173,18 @@ __global__ void PB_LB decode_kernel(const Code code, const Tables tb, const Deco
         float* stash = wm.scr + lane;
 #pragma unroll
         for (int k = 0; k < XW; ++k) if (k < xwn) stash[k * 32] = __uint_as_float(u[k]);
+        if (a.best_bits) {
+            // the MP lanes of a group share the unpacking of the winning word: lane s writes bytes [s*q, (s+1)*q)
+            const uint32_t bm = (__ballot_sync(kFull, p.alive && p.r == best_r) >> (lane & ~(MP - 1))) & Dec::GM;
+            const int bl = (lane & ~(MP - 1)) + (bm ? __ffs(bm) - 1 : 0);
+            __syncwarp();
+            const int q = ((K + MP - 1) / MP + 3) & ~3, s = lane & (MP - 1);
+            if (valid && s * q < K) write_info_bits(code, tb, wm.scr + bl, a.best_bits + frame * (int64_t)K, s * q, min(K, (s + 1) * q));
+        }
         if (p.alive) {
             if (a.cand) write_info_bits(code, tb, stash, a.cand + (frame * M + p.r) * (int64_t)K);
             if (a.metrics) a.metrics[frame * M + p.r] = p.m;
             if (p.r == best_r) {
-                if (a.best_bits) write_info_bits(code, tb, stash, a.best_bits + frame * (int64_t)K);
                 if (a.best_words) for (int k = 0; k < xwn; ++k) a.best_words[frame * xwn + k] = __float_as_uint(stash[k * 32]);
                 if (a.best_idx) a.best_idx[frame] = (int32_t)best_r;
                 if (a.crc_ok) a.crc_ok[frame] = (uint8_t)(code.crc_deg > 0 ? pass : 0);
