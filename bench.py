@@ -316,7 +316,7 @@ def main() -> None:
                               "issue slots busy (ncu, profiles/r01_v5_*) -- the gap is per-phase list management, not idle hardware"}
 
     extras = {}
-    if not args.no_extras and rank == 0:
+    if not args.no_extras and rank == 0 and world == 1:      # informational legs only on the single-GPU run
         extras = extra_legs(eng, llr, msg, dev, B)
 
     cb = cpu_baseline(args.cpu_sample) if (rank == 0 and world == 1) else None

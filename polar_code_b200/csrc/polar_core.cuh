@@ -8,9 +8,11 @@
 //
 // What replaces the reference's per-fork deep copies
 // (dl_scl_polar/polar/scl.py:52-62, 77 % of its run time):
-//   * LLR tree in shared memory, lane-interleaved: element (height h, index i)
-//     of slot `lane` lives at tree[(2^h-2+i)*32 + lane], so every access of a
-//     warp hits 32 distinct banks whatever slot each path points to.
+//   * LLR tree, lane-interleaved: element (height h, index i) of slot `lane`
+//     lives at base[(2^h-2+i)*32 + lane], so every access of a warp is one
+//     conflict-free / fully coalesced 128 B row whatever slot each path points
+//     to.  Heights < HS sit in shared memory, heights >= HS in an L2-resident
+//     global scratch (WarpMem), the height-1 pair of a phase pair in registers.
 //   * Lazy copy: a path keeps one 4-bit slot pointer per tree height (word P).
 //     Because every live path recomputes heights <= c in the same phase, a
 //     path always writes its OWN slot and a fork copies one register.
@@ -21,14 +23,13 @@
 //     re-encoded codeword x^, and u^ = x^ * F^{(x)n} (F^{(x)n} is an involution).
 //
 // Reference semantics kept bit-for-bit (scl.py:108-209): both children of a
-// free bit are scored with the exact softplus metric (scl.py:102-105), the
-// list is re-sorted after EVERY phase with a stable sort whose tie order is
-// (parent rank, bit) and truncated to M.  The stable order is obtained by
-// ranking unique 64-bit keys = (IEEE bits of the fp64 metric & ~15) | (2*rank+bit).
-// Metrics accumulate in fp64; LLR arithmetic is fp32 (f exact, g one rounding).
-// Frames in which two competing metrics come within ~1e-6 relative are flagged
-// (PB_FLAG_NEAR_TIE) -- these are the only frames allowed to differ from the
-// float64 reference.
+// free bit are scored with the exact softplus metric (scl.py:102-105) and the
+// list is truncated to the M best with the reference's stable order (parent
+// rank, bit).  The stable order is obtained by ranking unique 64-bit keys =
+// (IEEE bits of the fp64 metric & ~15) | (2*rank+bit).  Metrics accumulate in
+// fp64; LLR arithmetic is fp32 (f exact, g one rounding).  Frames in which two
+// competing metrics come within ~1e-6 relative are flagged (PB_FLAG_NEAR_TIE)
+// -- these are the only frames allowed to differ from the float64 reference.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -82,11 +83,11 @@ __device__ __forceinline__ float softplus_tail(float L) {
 
 // ---------------------------------------------------------------------------
 // Per-warp memory view.
-//   shared : tree heights 1..HSPLIT-1 (lane-interleaved), rank-exchange area, DL-SCL |L0| rows
-//   global : tree heights HSPLIT..n-1 (same lane-interleaved layout: one 128 B line per warp access) and the
-//            staged channel row when the LLRs are generated / de-rate-matched on the fly.  The scratch of all
-//            resident warps (~16 KB each) stays L2-resident; moving the two big heights out of shared memory is
-//            what lifts occupancy from 11 to ~28 warps per SM for N = 128.
+//   shared : tree heights 2..HS-1 (lane-interleaved), rank-exchange area, DL-SCL |L0| rows
+//   global : tree heights HS..n-1 (same lane-interleaved layout: one 128 B line per warp access) and the
+//            staged channel rows when the LLRs are generated / de-rate-matched on the fly.  The scratch of all
+//            resident warps (~16 KB each) stays L2-resident; moving the two tall heights out of shared memory is
+//            what lifts occupancy from 11 to 32 warps per SM for N = 128.
 // ---------------------------------------------------------------------------
 #ifdef PB_LAUNCH_BOUNDS
 #define PB_LB __launch_bounds__(PB_LAUNCH_BOUNDS)
@@ -119,9 +120,9 @@ constexpr int kXchgBytes = 32 * 16 + 32 * 2 * 4;   // candidate keys + rank-sort
 
 template <int MP, int HS = DefaultHS<MP>::value>
 struct WarpMem {
-    float* ts;            // shared tree base:  element (h,i), h <  HSPLIT, at ts[((2^h-2)+i)*32 + lane]
-    float* tg;            // global tree base (pre-offset): element (h,i), h >= HSPLIT, at tg[((2^h-2)+i)*32 + lane]
-    float* chan;          // [FPW][N+1] staged channel LLRs (global scratch); unused when rows are read in place
+    float* ts;            // shared tree base:  element (h,i), h <  HS, at ts[((2^h-2)+i)*32 + lane]
+    float* tg;            // global tree base (pre-offset): element (h,i), h >= HS, at tg[((2^h-2)+i)*32 + lane]
+    float* chan;          // [FPW][chan_stride(N)] staged channel LLRs (global scratch); unused when rows are read in place
     float* scr;           // >= 3*max(N/32,1) lane-interleaved rows of scratch for the encoder / bit stash
     unsigned long long* xchg;  // [32][2] candidate keys for the rank exchange / small per-frame scratch (shared)
     float* absl;          // [FPW][xk+1] DL-SCL only: |L0| of the reference path (flip.py:102) (shared)

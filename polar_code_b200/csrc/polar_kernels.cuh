@@ -31,7 +31,7 @@ struct DecodeArgs {
 };
 
 // NR rate matching: stage the de-rate-matched + de-interleaved row of each of the warp's FPW frames in wm.chan
-// ([f][N+1], global scratch).  rate_match.py:19-39: mean of the repeats, -1.0 where nothing was sent;
+// ([f][chan_stride(N)], global scratch).  rate_match.py:19-39: mean of the repeats, -1.0 where nothing was sent;
 // interleaver.py:26-37: gather through rm_src.  (Plain rows are read in place from the caller's buffer.)
 template <int MP, typename WM>
 __device__ __forceinline__ void load_channel(const Code& code, const Tables& tb, const WM& wm, const float* llr,
