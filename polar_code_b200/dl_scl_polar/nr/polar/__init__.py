@@ -1,14 +1,18 @@
-"""NR polar helpers on the B200 engine (reference: dl_scl_polar/nr/polar/__init__.py:3-14)."""
+"""NR polar helpers of the mirror package, served by the B200 engine.
 
-from .interleaver import subblock_interleave, subblock_deinterleave
-from .rate_match import rate_match_polar, derate_match_polar
-from .scl_nr import encode_rate_matched, decode_rate_matched_scl
+Public surface = the reference's (dl_scl_polar/nr/polar/__init__.py:3-14): two (de)interleaver index maps, two
+rate-matching helpers and the fused rate-matched encode / SCL decode."""
 
-__all__ = [
-    "subblock_interleave",
-    "subblock_deinterleave",
-    "rate_match_polar",
-    "derate_match_polar",
-    "encode_rate_matched",
-    "decode_rate_matched_scl",
-]
+from . import interleaver as _ilv, rate_match as _rm, scl_nr as _nr
+
+_EXPORTS = {
+    _ilv: ("subblock_interleave", "subblock_deinterleave"),
+    _rm: ("rate_match_polar", "derate_match_polar"),
+    _nr: ("encode_rate_matched", "decode_rate_matched_scl"),
+}
+__all__ = []
+for _mod, _names in _EXPORTS.items():
+    for _name in _names:
+        globals()[_name] = getattr(_mod, _name)
+        __all__.append(_name)
+del _mod, _names, _name
