@@ -22,10 +22,9 @@ static int ensure_queues(pb200_engine* e, long long frames, int retries, bool wa
         e->llr_store_bytes = need_store;
     }
     if (e->q_bytes < need) {
-        cudaFree(e->d_q[0]); cudaFree(e->d_q[1]);
-        e->d_q[0] = e->d_q[1] = nullptr; e->q_bytes = 0;
+        cudaFree(e->d_q[0]);
+        e->d_q[0] = nullptr; e->q_bytes = 0;
         CUDA_TRY(cudaMalloc((void**)&e->d_q[0], need));
-        CUDA_TRY(cudaMalloc((void**)&e->d_q[1], need));
         e->q_bytes = need;
     }
     if (e->q_counts_n < retries + 2) {
@@ -78,9 +77,15 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
     code.M = M;
     const void* base = big ? pb_sweep_kernel_9(MP, false) : pb_sweep_kernel_7(MP, false);
     const void* round = big ? pb_sweep_kernel_9(MP, true) : pb_sweep_kernel_7(MP, true);
-    KernelCfg kb, kr;
+    KernelCfg kb, kr{};
     int rc = choose_cfg(e, base, MP, 4, warp_bytes(MP, code.N, 0), &kb);
     if (rc) return rc;
+    int rgrid = 0;
+    if (a.retries > 0) {
+        rc = choose_cfg(e, round, MP, 5, warp_bytes(MP, code.N, code.K, true), &kr);
+        if (rc) return rc;
+        rgrid = std::max(1, e->sms * kr.ctas_per_sm);
+    }
     const int fpw = 32 / MP;
     // pieces of 4 Mi frames: with retries every queued frame keeps its LLR row (N floats) in the store, so the
     // worst case (every frame fails) is 4 Mi x N x 4 B = 2 GB for N = 128 -- allocated lazily, grown on demand
@@ -123,29 +128,22 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
         const long long groups = (nf + fpw - 1) / fpw;
         const long long want = (groups + kb.wpc - 1) / kb.wpc;
         const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)e->sms * kb.ctas_per_sm));
-        rc = ensure_scratch(e, st, (size_t)grid * kb.wpc, MP, &p.gscratch);
+        rc = ensure_scratch(e, st, (size_t)std::max(rgrid * kr.wpc, grid * kb.wpc), MP, &p.gscratch);
         if (rc) return rc;
         {
             void* args[3] = {(void*)&code, (void*)&e->tb, (void*)&p};
             CUDA_TRY(cudaLaunchKernel(base, dim3(grid), dim3(kb.wpc * 32), args, kb.smem, st));
         }
         if (a.retries > 0) {
-            rc = choose_cfg(e, round, MP, 5, warp_bytes(MP, code.N, code.K, true), &kr);
-            if (rc) return rc;
-            const long long rgroups = (nf + fpw - 1) / fpw;
-            const long long rwant = (rgroups + kr.wpc - 1) / kr.wpc;
-            const int rgrid = (int)std::max<long long>(1, std::min<long long>(rwant, (long long)e->sms * kr.ctas_per_sm));
-            rc = ensure_scratch(e, st, (size_t)std::max(rgrid * kr.wpc, grid * kb.wpc), MP, &p.gscratch);
-            if (rc) return rc;
-            for (int r = 0; r < a.retries; ++r) {
-                SweepArgs q = p;
-                q.q_in = e->d_q[r & 1];
-                q.q_in_count = e->d_q_counts + r;
-                q.q_out = e->d_q[(r + 1) & 1];
-                q.q_out_count = e->d_q_counts + r + 1;
-                void* args[3] = {(void*)&code, (void*)&e->tb, (void*)&q};
-                CUDA_TRY(cudaLaunchKernel(round, dim3(rgrid), dim3(kr.wpc * 32), args, kr.smem, st));
-            }
+            // one persistent retry launch: groups pull failed frames from the queue the baseline pass filled
+            // (count at d_q_counts[0]) through the cursor d_q_counts[1] and keep each frame until it is done
+            SweepArgs q = p;
+            q.q_in = e->d_q[0];
+            q.q_in_count = e->d_q_counts;
+            q.q_out = nullptr;
+            q.q_out_count = e->d_q_counts + 1;
+            void* args[3] = {(void*)&code, (void*)&e->tb, (void*)&q};
+            CUDA_TRY(cudaLaunchKernel(round, dim3(rgrid), dim3(kr.wpc * 32), args, kr.smem, st));
         }
     }
     return PB200_OK;

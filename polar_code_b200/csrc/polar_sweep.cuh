@@ -4,11 +4,12 @@
 // Reference paths: eval/run_fer_sweep.py:60-121 (channel, counters), eval/run_ber_sweep.py:112-181,
 // dlscl/flip.py:65-141 (retry controller), nr/polar/scl_nr.py:23-57 (rate-matched chain).
 //
-// DL-SCL on the GPU: the baseline pass decodes every frame; frames whose best path fails the CRC are appended
-// to a queue (frame id, best u-hat, tried set).  Each retry round is one launch over the compacted queue:
-// regenerate (Philox) or reload the frame's LLRs, replay the reference path to get |L0| (flip.py:102,133),
-// score q = |L0| @ beta in fp64 (flip.py:104-108), force the prefix + flipped bit (flip.py:30-34), decode, and
-// either finish the frame or append it to the next round's queue.  All lanes stay busy whatever the SNR.
+// DL-SCL on the GPU: the baseline pass decodes every frame; frames whose best path fails the CRC are appended to
+// a queue (frame id, best u-hat, transmitted word, their LLR row goes to the LLR store).  ONE persistent retry
+// kernel then drains the queue: every lane group owns a frame through all of its retries -- replay the reference
+// path to get |L0| (flip.py:102,133), score q = |L0| @ beta in fp64 (flip.py:104-108), force the prefix + flipped
+// bit (flip.py:30-34), list-decode, finish or go on -- and pulls the next entry when its frame is done, so all
+// lanes stay busy whatever the SNR and nothing is regenerated or re-queued between retries.
 #pragma once
 #include "polar_kernels.cuh"
 
@@ -479,10 +480,15 @@ __global__ void __launch_bounds__(768) sweep_kernel(const Code code, const Table
 }
 
 // ---------------------------------------------------------------------------------------------------
-// One DL-SCL retry round over the compacted queue (flip.py:110-135).
+// DL-SCL retries (flip.py:110-135): ONE persistent launch over the queue of frames whose baseline decode failed.
+// Every lane group owns one frame at a time and keeps it through all of its retries (reference bits, tried set,
+// flags live in registers); a group whose frame is finished pulls the next queue entry (warp-aggregated atomic),
+// so all lanes stay busy until the queue is drained and there are no per-round launches or queue round trips.
+// Per retry: replay the reference path for |L0| (flip.py:102,133), rank q = |L0| @ beta in fp64 (flip.py:104-108),
+// force prefix + flipped bit (flip.py:30-34), list-decode (flip.py:53), then finish or go on (flip.py:127-135).
 // ---------------------------------------------------------------------------------------------------
 template <int MP, int LOGMAX, int HS = 5>
-__global__ void __launch_bounds__(640) dl_round_kernel(const Code code, const Tables tb, const SweepArgs a) {
+__global__ void __launch_bounds__(640) dl_retry_kernel(const Code code, const Tables tb, const SweepArgs a) {
     using S = Sweep<MP, LOGMAX, HS>;
     using WM = WarpMem<MP, HS>;
     using PathT = typename S::PathT;
@@ -492,35 +498,53 @@ __global__ void __launch_bounds__(640) dl_round_kernel(const Code code, const Ta
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     WM wm;
     wm.carve(smem + (size_t)warp * WM::bytes(code.N, code.K), a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WM::gbytes(code.N), code.N);
-    const int slot = lane & (MP - 1), fme = lane / MP;
+    const int slot = lane & (MP - 1), fme = lane / MP, gbase = lane & ~(MP - 1);
     const bool leader = slot == 0;
     const int K = code.K;
     uint32_t acc[cNum];
 #pragma unroll
     for (int c = 0; c < cNum; ++c) acc[c] = 0;
     const unsigned int n_in = min(*a.q_in_count, a.q_capacity);
-    const long long ngroups = ((long long)n_in + FPW - 1) / FPW;
-    for (long long g = (long long)blockIdx.x * wpc + warp; g < ngroups; g += (long long)gridDim.x * wpc) {
-        const long long idx = g * FPW + fme;
-        const bool valid = idx < (long long)n_in;
-        long long my_frame = -1, store = 0;
-        uint32_t eflags = 0, n_tried = 0;
-        uint32_t u_ref[XW], tried[XW], u_sent[XW];
+
+    // state of the frame this group is working on (identical on all lanes of the group)
+    bool active = false, exhausted = false;
+    long long my_frame = -1, store = 0;
+    uint32_t eflags = 0, n_tried = 0;
+    uint32_t u_ref[XW], tried[XW], u_sent[XW];
 #pragma unroll
-        for (int k = 0; k < XW; ++k) { u_ref[k] = 0; tried[k] = 0; u_sent[k] = 0; }
-        if (valid) {
-            const Entry* e = reinterpret_cast<const Entry*>(a.q_in) + idx;
-            my_frame = e->h.frame; eflags = e->h.flags; n_tried = e->h.n_tried; store = e->store;
+    for (int k = 0; k < XW; ++k) { u_ref[k] = 0; tried[k] = 0; u_sent[k] = 0; }
+
+    for (;;) {
+        // ---- idle groups pull the next queue entry --------------------------------------------------------
+        {
+            const uint32_t want = __ballot_sync(kFull, leader && !active && !exhausted);
+            if (want) {
+                unsigned int base = 0;
+                if (lane == 0) base = atomicAdd(a.q_out_count, (unsigned int)__popc(want));     // q_out_count = "next entry" cursor
+                base = __shfl_sync(kFull, base, 0);
+                long long idx = -1;
+                if (leader && !active && !exhausted) idx = (long long)base + __popc(want & ((1u << lane) - 1u));
+                idx = __shfl_sync(kFull, idx, gbase);
+                if (idx >= 0) {
+                    if (idx < (long long)n_in) {
+                        const Entry* e = reinterpret_cast<const Entry*>(a.q_in) + idx;
+                        my_frame = e->h.frame; eflags = e->h.flags; n_tried = e->h.n_tried; store = e->store;
 #pragma unroll
-            for (int k = 0; k < XW; ++k) { u_ref[k] = e->u[k]; tried[k] = e->tried[k]; u_sent[k] = e->u_sent[k]; }
+                        for (int k = 0; k < XW; ++k) { u_ref[k] = e->u[k]; tried[k] = e->tried[k]; u_sent[k] = e->u_sent[k]; }
+                        active = true;
+                    } else exhausted = true;
+                }
+            }
         }
-        // channel row of this frame: the caller's buffer (API mode), the LLR store (sweep mode), or -- with NR rate
+        if (!__any_sync(kFull, active)) break;
+        const bool valid = active;
+        // channel row of this frame: the LLR store (sweep mode), the caller's buffer (API mode), or -- with NR rate
         // matching in API mode -- the de-rate-matched row staged by load_channel_ids
         const float* chanf;
-        if (a.llr == nullptr) chanf = a.llr_store + store * (long long)code.N;
+        if (a.llr == nullptr) chanf = a.llr_store + (valid ? store : 0) * (long long)code.N;
         else if (tb.E == 0) chanf = a.llr + (valid ? (my_frame - a.frame_begin) : 0) * (long long)a.in_len;
         else {
-            load_channel_ids<MP, WM>(code, tb, wm, a.llr, a.in_len, my_frame, a.frame_begin, lane);
+            load_channel_ids<MP, WM>(code, tb, wm, a.llr, a.in_len, valid ? my_frame : -1, a.frame_begin, lane);
             chanf = wm.chan + fme * chan_stride(code.N);
         }
         // |L0| of the reference path (flip.py:102,133): replay it and keep the info-phase leaf LLRs
@@ -569,9 +593,9 @@ __global__ void __launch_bounds__(640) dl_round_kernel(const Code code, const Ta
             if (om1 < m1 || (om1 == m1 && oa1 < a1)) { m2 = fmin(m1, om2); m1 = om1; a1 = oa1; }
             else m2 = fmin(m2, om1);
         }
-        const int jf = valid ? a1 : 0;
+        const int jf = (valid && a1 < K) ? a1 : 0;
         if (valid && m2 < 1e299 && (m2 - m1) <= 2e-6 * fmax(fabs(m1), fabs(m2))) eflags |= PB_FLAG_RANK_TIE;
-        const int pf = (jf < K) ? (int)__ldg(&tb.info_pos[jf]) : 0;
+        const int pf = (int)__ldg(&tb.info_pos[jf]);
         // _force_vector (flip.py:30-34): prefix of the reference bits, then the flipped bit, rest free
         uint32_t fm[XW], fv[XW];
 #pragma unroll
@@ -581,9 +605,9 @@ __global__ void __launch_bounds__(640) dl_round_kernel(const Code code, const Ta
             const uint32_t bit = (pf >= lo && pf < lo + 32) ? (1u << (pf - lo)) : 0u;
             fm[w] = code.info_mask[w] & (below | bit);
             fv[w] = (u_ref[w] & below) | (~u_ref[w] & bit);
-            if (jf >= lo && jf < lo + 32) tried[w] |= 1u << (jf - lo);      // tried set is indexed by info index
+            if (valid && jf >= lo && jf < lo + 32) tried[w] |= 1u << (jf - lo);      // tried set is indexed by info index
         }
-        n_tried += 1;
+        if (valid) n_tried += 1;
         if (leader && valid && a.tried) a.tried[(my_frame - a.frame_begin) * (long long)a.R + (n_tried - 1)] = jf;
         uint32_t flags = 0;
         PathT p;
@@ -591,14 +615,20 @@ __global__ void __launch_bounds__(640) dl_round_kernel(const Code code, const Ta
         S::DecF::run(code, tb.info_mask, wm, p, lane, chanf, fm, fv, flags); // retry_with_flip (flip.py:37-62)
         typename S::Best b;
         S::pick_best(code, tb, p, lane, flags | eflags, b);
-        bool need = false;
-        if (leader && valid) {
-            acc[cNearTie] += ((b.flags & PB_FLAG_NEAR_TIE) && !(eflags & PB_FLAG_NEAR_TIE)) ? 1u : 0u;
+        if (valid) {
+            if (leader) acc[cNearTie] += ((b.flags & PB_FLAG_NEAR_TIE) && !(eflags & PB_FLAG_NEAR_TIE)) ? 1u : 0u;
             const bool pass = code.crc_deg == 0 ? true : b.pass;
-            need = !(pass || (int)n_tried >= a.retries || (int)n_tried >= K);   // flip.py:111,134
-            if (!need) S::finish_dl(code, tb, a, wm, lane, my_frame, b, n_tried, u_sent, acc);
+            const bool more = !(pass || (int)n_tried >= a.retries || (int)n_tried >= K);   // flip.py:111,134
+            if (!more) {
+                if (leader) S::finish_dl(code, tb, a, wm, lane, my_frame, b, n_tried, u_sent, acc);
+                active = false;
+            } else {
+                // the next attempt starts from THIS attempt's best path (flip.py:127-133)
+                eflags = b.flags;
+#pragma unroll
+                for (int k = 0; k < XW; ++k) u_ref[k] = b.u[k];
+            }
         }
-        S::enqueue(code, a, lane, need, my_frame, b, tried, n_tried, u_sent, store, chanf);
         __syncwarp();
     }
     S::flush(a, lane, acc);
