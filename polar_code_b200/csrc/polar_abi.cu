@@ -322,7 +322,7 @@ static int ensure_scratch(pb200_engine* e, cudaStream_t st, size_t warps, int MP
     return PB200_OK;
 }
 
-// shared bytes per warp; round = DL-SCL round kernel (HS = 5), otherwise the kernel's default split
+// shared bytes per warp; round = DL-SCL retry kernel (HS = 5, holds the |L0| rows), otherwise the kernel's default split
 static size_t warp_bytes(int MP, int N, int xk, bool round = false) {
     if (round) {
         switch (MP) {

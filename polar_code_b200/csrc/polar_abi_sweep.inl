@@ -1,4 +1,4 @@
-// polar_abi_sweep.inl -- host side of the Monte-Carlo sweep, DL-SCL rounds, channel generator, NR encoder.
+// polar_abi_sweep.inl -- host side of the Monte-Carlo sweep, DL-SCL retry kernel, channel generator, NR encoder.
 // Included at the end of polar_abi.cu.
 
 int sweep_build_tables(pb200_engine* e) {

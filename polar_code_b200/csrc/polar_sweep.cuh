@@ -1,5 +1,5 @@
 // polar_sweep.cuh -- channel generation (Philox4x32-10 + Box-Muller), the fused Monte-Carlo sweep kernel and
-// DL-SCL flip retries as queue-compacted rounds.
+// DL-SCL flip retries as one persistent, work-stealing retry kernel.
 //
 // Reference paths: eval/run_fer_sweep.py:60-121 (channel, counters), eval/run_ber_sweep.py:112-181,
 // dlscl/flip.py:65-141 (retry controller), nr/polar/scl_nr.py:23-57 (rate-matched chain).
@@ -253,7 +253,7 @@ __device__ __forceinline__ void gen_channel(const Code& code, const Tables& tb, 
 }
 
 
-// Gather-load of channel LLRs for arbitrary frame ids (LLR-in mode of the DL-SCL rounds).
+// Gather-load of channel LLRs for arbitrary frame ids (LLR-in mode of the DL-SCL retry kernel).
 template <int MP, typename WM>
 __device__ __forceinline__ void load_channel_ids(const Code& code, const Tables& tb, const WM& wm, const float* llr,
                                                  int in_len, long long my_frame, long long frame_begin, int lane) {

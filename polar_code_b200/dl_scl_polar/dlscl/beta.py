@@ -3,7 +3,7 @@
 Interface of the reference's `SymmetricBeta` (dl_scl_polar/dlscl/beta.py:9-46): parameter `off_diag` [dim,dim],
 `beta_matrix()` = I + U + U^T with U the strict upper triangle of `off_diag`, `forward(x)` = x @ beta for a vector
 or a batch, `clamp_diagonal()` zeroes the unused diagonal of the raw parameter.  The engine's retry rounds only
-consume the exported float32 `.npy` (csrc/polar_sweep.cuh, dl_round_kernel)."""
+consume the exported float32 `.npy` (csrc/polar_sweep.cuh, dl_retry_kernel)."""
 
 from __future__ import annotations
 

@@ -63,7 +63,7 @@ def decode_with_retries(
 ) -> dict:
     """Baseline SCL plus up to ``retries`` beta-ranked flips (flip.py:65-141).
 
-    The retry rounds (replay of the reference path, |L0| @ beta ranking, forced decode) run fused on the GPU
+    The retries (replay of the reference path, |L0| @ beta ranking, forced decode) run fused on the GPU
     (csrc/polar_sweep.cuh); the per-attempt dictionaries of the reference's ``attempts`` list are then
     materialised with one decode_scl call per attempt along the flip indices the kernel chose."""
     if M <= 0:
