@@ -81,3 +81,31 @@ def test_dlscl_generic_matches_oracle(N, K, poly, M, retries):
         assert not (~same & ((flags & 3) == 0)).any(), f"unflagged DL-SCL mismatch N={N} M={M}"
         assert (~same).sum() <= 6
         assert ref["n_attempts"].max() > 1
+
+
+def test_dlscl_through_rate_matched_input():
+    """DL-SCL on E-long rate-matched LLRs (de-rate-match + de-interleave fused into the retry kernel's load) equals the
+    oracle's decode_with_retries on the oracle's de-rate-matched vector."""
+    from polar_code_b200.engine import PolarEngine
+    rng = np.random.default_rng(99)
+    N, K, E, M, poly = 128, 88, 256, 4, "0x1864CFB"
+    A = O.construct_info_set(N, K)
+    eng = PolarEngine(N, A, poly)
+    eng.set_rate_matching(E)
+    nv = O.noise_var_ber(3.5, 64, E)
+    rows, internal = [], []
+    for _ in range(600):
+        _, l = O.ber_frame(rng, "nr_polar_scl", 64, 24, poly, N, E, A, nv)
+        l32 = l.astype(np.float32)
+        rows.append(l32)
+        internal.append(O.subblock_deinterleave(O.derate_match(l32.astype(np.float64), N), N))
+    rows = np.array(rows)
+    ref = O.dlscl_decode_batch(np.array(internal), A, M, 8, crc=poly)
+    out = eng.dlscl_decode(rows, M, 8)
+    flags = out["flags"].cpu().numpy()
+    same = ((out["best_bits"].cpu().numpy().astype(np.int8) == ref["best_bits"]).all(axis=1)
+            & (out["success"].cpu().numpy().astype(bool) == ref["success"])
+            & (out["n_attempts"].cpu().numpy() == ref["n_attempts"])
+            & (out["tried"].cpu().numpy() == ref["tried"]).all(axis=1))
+    assert not (~same & ((flags & 3) == 0)).any()
+    assert (~same).sum() <= 6 and ref["n_attempts"].max() > 2
