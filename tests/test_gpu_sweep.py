@@ -196,3 +196,27 @@ def test_host_buffer_path_matches_device_path(eng):
     eng.scl_decode_host(h_llr, 4, h_bits, h_ok, h_fl)
     assert torch.equal(h_bits, ref["best_bits"].cpu()) and torch.equal(h_ok, ref["crc_ok"].cpu())
     assert torch.equal(h_fl, ref["flags"].cpu())
+
+
+@pytest.mark.parametrize("M,snr", [(4, 4.5), (1, 5.0), (8, 4.0)])
+def test_fer_matches_oracle_on_reference_channel(eng, g128, M, snr):
+    """FER / BER of the GPU sweep (Philox channel, 1e7 frames) against the float64 oracle fed by the reference's own
+    PCG64 channel loop (run_fer_sweep.py:60-121 restated in oracle.fer_sweep_frames, 2e5 frames): SCL and DL-SCL
+    frame-error rates and the SCL bit-error rate agree within 4 binomial sigmas of the smaller sample."""
+    n_ref, n = 200_000, 10_000_000
+    msgs, llrs, _ = O.fer_sweep_frames(snr, n_ref, seed=12345)
+    A = g128["info_set"]
+    s = O.scl_decode_batch(llrs, A, M, crc=CRC24, want_info_llrs=False)
+    d = O.dlscl_decode_batch(llrs, A, M, 8, crc=CRC24, beta=None)
+    ok_scl = np.array([O.check_crc(b, CRC24) for b in s["best_bits"]])
+    ref = {"fer_scl": 1 - ok_scl.mean(), "fer_dl": 1 - d["success"].mean(),
+           "ber_scl": (s["best_bits"] != msgs).mean(), "work": (d["n_attempts"] - 1).mean()}
+    c = _counters(eng, M=M, noise_var=_nv(snr), n_frames=n, seed=777, stream_id=int(snr * 10), k_payload=40, retries=8)
+    est = {"fer_scl": c[1] / n, "fer_dl": c[3] / n, "ber_scl": c[2] / (n * 64), "work": c[7] / n}
+    for k in ("fer_scl", "fer_dl"):
+        p = est[k]
+        sigma = math.sqrt(p * (1 - p) / n_ref)
+        assert abs(ref[k] - p) < 4 * sigma, (k, ref[k], p, sigma)
+    # bit errors come in bursts (a wrong frame has ~10 wrong bits): scale sigma by the frame-level dispersion
+    assert abs(ref["ber_scl"] - est["ber_scl"]) < 4 * est["ber_scl"] / math.sqrt(max(est["fer_scl"] * n_ref, 1))
+    assert abs(ref["work"] - est["work"]) < 0.05 * max(est["work"], 1e-3) + 4e-3
