@@ -12,6 +12,8 @@ Fixtures written:
   scl_toy.npz    N=16,K=12 poly 0x17 (tests/test_ber_eval.py geometry), N=8, N=32
   nr_p128.npz    NR chain E=256 and E=96 -> N=128, K=88, decode_rate_matched_scl
   published.json rows of results/fer_M{1,4,8}.csv + the recipe that reproduces them
+  ldpc.npz       nr/ldpc: H matrices, encode_ldpc, derate_match_ldpc, decode_ldpc_nms outputs and rows of the
+                 reference's own run_ber_sweep --scheme nr_ldpc (``python oracle/gen_golden.py ldpc`` writes only this)
 """
 
 from __future__ import annotations
@@ -204,10 +206,82 @@ def gen_published():
     (OUT / "published.json").write_text(json.dumps({"rows": rows, "recipe": recipe}, indent=1))
 
 
+def gen_ldpc():
+    """nr/ldpc fixtures from the reference."""
+    import types
+    from dl_scl_polar.nr.ldpc import (load_base_graph, build_h_matrix, encode_ldpc, rate_match_ldpc,
+                                      derate_match_ldpc, decode_ldpc_nms)
+    rng = np.random.default_rng(23)
+    out = {}
+    for bg, Z in [(1, 2), (2, 2), (2, 4), (1, 8), (2, 32)]:
+        out[f"H_bg{bg}_Z{Z}"] = build_h_matrix(load_base_graph(bg), Z)
+    # encoder + decoder on noisy frames; LLRs are float32-representable doubles
+    for Z, E, snr_db, max_iter, alpha, tag in [(2, 12, 3.0, 20, 0.8, "z2"), (4, 24, 2.0, 20, 0.8, "z4"),
+                                               (8, 61, 1.0, 10, 0.9, "z8e61"), (8, 130, -1.0, 20, 0.8, "z8e130"),
+                                               (32, 384, -1.5, 20, 0.8, "z32e384"), (4, 24, 1.0, 0, 0.8, "z4it0"),
+                                               (4, 24, 0.0, 3, 0.75, "z4it3")]:
+        H = build_h_matrix(load_base_graph(2), Z)
+        n = H.shape[1]
+        k = n - H.shape[0]
+        nv = 1.0 / (2.0 * 10 ** (snr_db / 10.0) * k / E)
+        pays, codes, llrs, ders, hards, its, oks = [], [], [], [], [], [], []
+        for _ in range(24):
+            payload = rng.integers(0, 2, size=k, dtype=np.int8)
+            cw = encode_ldpc(payload, H)
+            tx = rate_match_ldpc(cw, E)
+            y = 1.0 - 2.0 * tx.astype(np.float64) + rng.normal(0.0, np.sqrt(nv), size=E)
+            l = (2.0 * y / nv).astype(np.float32).astype(np.float64)
+            d = derate_match_ldpc(l, n)
+            r = decode_ldpc_nms(d, H, max_iter=max_iter, alpha=alpha)
+            pays.append(payload); codes.append(cw); llrs.append(l); ders.append(d)
+            hards.append(r["hard"]); its.append(r["iters_used"]); oks.append(r["parity_ok"])
+        out[f"{tag}_cfg"] = np.array([Z, E, max_iter], np.int64)
+        out[f"{tag}_alpha"] = np.array([alpha])
+        out[f"{tag}_payload"] = np.array(pays, np.int8)
+        out[f"{tag}_code"] = np.array(codes, np.int8)
+        out[f"{tag}_llr"] = np.array(llrs, np.float64)
+        out[f"{tag}_derated"] = np.array(ders, np.float64)
+        out[f"{tag}_hard"] = np.array(hards, np.int8)
+        out[f"{tag}_iters"] = np.array(its, np.int32)
+        out[f"{tag}_ok"] = np.array(oks, np.int8)
+    # no early stop
+    H = build_h_matrix(load_base_graph(2), 4)
+    r = [decode_ldpc_nms(l, H, max_iter=6, alpha=0.8, early_stop=False) for l in out["z4_derated"]]
+    out["z4_noearly_hard"] = np.array([x["hard"] for x in r], np.int8)
+    out["z4_noearly_iters"] = np.array([x["iters_used"] for x in r], np.int32)
+    out["z4_noearly_ok"] = np.array([x["parity_ok"] for x in r], np.int8)
+    # the reference's own CLI loop (PCG64 stream): rows of run_ber_sweep.run for two small nr_ldpc set-ups
+    mpl = types.ModuleType("matplotlib"); mpl.use = lambda *a, **k: None
+    plt = types.ModuleType("matplotlib.pyplot")
+    for name in ("figure", "semilogy", "xlabel", "ylabel", "grid", "legend", "tight_layout", "savefig", "close"):
+        setattr(plt, name, lambda *a, **k: None)
+    mpl.pyplot = plt
+    sys.modules.setdefault("matplotlib", mpl); sys.modules.setdefault("matplotlib.pyplot", plt)
+    from dl_scl_polar.eval import run_ber_sweep
+    cli = {
+        "cli_a": ["--scheme", "nr_ldpc", "--K_payload", "6", "--K_crc", "0", "--E", "12", "--bg", "2", "--Z", "2",
+                  "--EbN0_lo", "2.0", "--EbN0_hi", "4.0", "--EbN0_step", "1.0", "--bits_cap", "6000", "--err_cap", "60",
+                  "--out", "/tmp/_ldpc_a.csv", "--crc_poly", "0x1", "--seed", "3"],
+        "cli_b": ["--scheme", "nr_ldpc", "--K_payload", "20", "--K_crc", "4", "--E", "70", "--bg", "1", "--Z", "8",
+                  "--EbN0_lo", "1.0", "--EbN0_hi", "2.0", "--EbN0_step", "1.0", "--bits_cap", "8000", "--err_cap", "50",
+                  "--max_iter", "12", "--alpha", "0.75", "--out", "/tmp/_ldpc_b.csv", "--crc_poly", "0x17", "--seed", "5"],
+    }
+    cli_rows = {}
+    for tag, argv in cli.items():
+        rows = run_ber_sweep.run(run_ber_sweep.parse_args(argv))
+        cli_rows[tag] = {"argv": argv, "rows": [{k: (v if isinstance(v, str) else float(v)) for k, v in r.items()} for r in rows]}
+    out["cli_json"] = np.frombuffer(json.dumps(cli_rows).encode(), np.uint8)
+    np.savez_compressed(OUT / "ldpc.npz", **out)
+
+
 if __name__ == "__main__":
     OUT.mkdir(parents=True, exist_ok=True)
+    if sys.argv[1:] == ["ldpc"]:
+        gen_ldpc(); print("ldpc done")
+        sys.exit(0)
     gen_p128(); print("p128 done")
     gen_toy(); print("toy done")
     gen_nr(); print("nr done")
     gen_published()
+    gen_ldpc(); print("ldpc done")
     print("golden vectors written to", OUT)

@@ -1,7 +1,7 @@
 """ctypes front-end of the CPU ORACLE (test infrastructure, NOT the product).
 
-Loads ``oracle/build/libpolar_oracle.so`` (built from ``polar_oracle.c`` by
-``oracle/Makefile``) and exposes NumPy-level helpers that mirror the reference's
+Loads ``oracle/build/libpolar_oracle.so`` (built from ``polar_oracle.c`` and
+``ldpc_oracle.c`` by ``oracle/Makefile``) and exposes NumPy-level helpers that mirror the reference's
 functions.  Only ``tests/``, ``bench.py``'s CPU-baseline legs and
 ``__graft_entry__.smoke()`` may import this module, and only as the checker.
 
@@ -11,6 +11,7 @@ CSV can be regenerated on a box where ``/root/reference`` does not exist:
 
 * ``fer_sweep_frames``  -> ``dl_scl_polar/eval/run_fer_sweep.py:60-121``
 * ``ber_sweep_frames``  -> ``dl_scl_polar/eval/run_ber_sweep.py:112-142,228-291``
+* ``ldpc_ber_point``    -> the same loop for ``--scheme nr_ldpc`` (:134-136,258-271)
 """
 
 from __future__ import annotations
@@ -45,8 +46,8 @@ class _DlInfo(C.Structure):
 
 def build(force: bool = False) -> Path:
     """Compile the C restatement (gcc); building the checker is not using it."""
-    src = _HERE / "polar_oracle.c"
-    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src.stat().st_mtime:
+    newest = max((_HERE / f).stat().st_mtime for f in ("polar_oracle.c", "ldpc_oracle.c", "Makefile"))
+    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < newest:
         subprocess.check_call(["make", "-s", "-C", str(_HERE)])
     return _LIB_PATH
 
@@ -315,3 +316,94 @@ def ber_frame(rng, scheme: str, K_payload: int, K_crc: int, crc_poly: str, N: in
     symbols = 1.0 - 2.0 * tx
     noise = rng.normal(0.0, math.sqrt(noise_var), size=symbols.shape)
     return payload, 2.0 * (symbols + noise) / noise_var
+
+
+# ----------------------------------------------------------------------------
+# nr/ldpc (toy NR-LDPC family)
+# ----------------------------------------------------------------------------
+
+def ldpc_build_h(bg: int, Z: int) -> np.ndarray:
+    """basegraphs.py:39-42 + builder.py:20-30"""
+    if Z <= 0:
+        raise ValueError("Z must be positive")
+    H = np.zeros((3 * Z, 6 * Z), np.int8)
+    m, n = C.c_int(), C.c_int()
+    if lib().po_ldpc_build_h(C.c_int(bg), C.c_int(Z), _ptr(H, C.c_int8), C.byref(m), C.byref(n)) != 0:
+        raise ValueError(f"Unknown base graph: {bg}")
+    return H
+
+
+def ldpc_encode(payload: np.ndarray, H: np.ndarray) -> np.ndarray:
+    """encode.py:52-66"""
+    payload = np.ascontiguousarray(payload, np.int8)
+    H = np.ascontiguousarray(H, np.int8)
+    m, n = H.shape
+    out = np.zeros(n, np.int8)
+    rc = lib().po_ldpc_encode(_ptr(payload, C.c_int8), C.c_int(payload.size), _ptr(H, C.c_int8), C.c_int(m), C.c_int(n),
+                              _ptr(out, C.c_int8))
+    if rc == -1:
+        raise ValueError("Parity-check matrix too small for payload length")
+    if rc != 0:
+        raise ValueError("Linear system over GF(2) has no solution")
+    return out
+
+
+def ldpc_rate_match(codeword: np.ndarray, E: int) -> np.ndarray:
+    """rate_match.py:8-15"""
+    N = codeword.size
+    if E <= N:
+        return codeword[:E]
+    return np.tile(codeword, (E + N - 1) // N)[:E]
+
+
+def ldpc_derate_match(llr: np.ndarray, N: int) -> np.ndarray:
+    """rate_match.py:18-38"""
+    llr = np.ascontiguousarray(llr, np.float64)
+    out = np.zeros(N, np.float64)
+    lib().po_ldpc_derate(_ptr(llr, C.c_double), C.c_int(llr.size), C.c_int(N), _ptr(out, C.c_double))
+    return out
+
+
+def ldpc_decode_batch(llr, H, max_iter: int = 20, alpha: float = 0.8, early_stop: bool = True):
+    """decode_nms.py:8-40 over llr[B,n] -> hard[B,n] int8, iters_used[B], parity_ok[B]."""
+    llr = np.ascontiguousarray(np.atleast_2d(llr), np.float64)
+    H = np.ascontiguousarray(H, np.int8)
+    m, n = H.shape
+    B = llr.shape[0]
+    if llr.shape[1] != n:
+        raise ValueError("llr length mismatch")
+    hard = np.zeros((B, n), np.int8)
+    iters = np.zeros(B, np.int32)
+    ok = np.zeros(B, np.int32)
+    lib().po_ldpc_decode_batch(_ptr(llr, C.c_double), C.c_int(B), _ptr(H, C.c_int8), C.c_int(m), C.c_int(n),
+                               C.c_int(max_iter), C.c_double(alpha), C.c_int(int(early_stop)), _ptr(hard, C.c_int8),
+                               _ptr(iters, C.c_int32), _ptr(ok, C.c_int32))
+    return {"hard": hard, "iters_used": iters, "parity_ok": ok.astype(bool)}
+
+
+def ldpc_ber_point(rng, EbN0_dB: float, *, K_payload: int, K_crc: int, crc_poly: str, H: np.ndarray, E: int,
+                   max_iter: int, alpha: float, err_cap: int, bits_cap: float):
+    """One Eb/N0 point of run_ber_sweep.py:112-181 for --scheme nr_ldpc (encoder/decoder of :258-271), consuming
+    `rng` exactly like the reference.  Returns (bits_total, bit_errors, frame_errors, frames, work_sum)."""
+    n = H.shape[1]
+    k = n - H.shape[0]
+    nv = noise_var_ber(EbN0_dB, K_payload, E)
+    sg = math.sqrt(nv)
+    bits_total = bit_errors = frame_errors = frames = 0
+    work = 0.0
+    while bit_errors < err_cap and bits_total < bits_cap:
+        payload = rng.integers(0, 2, size=K_payload, dtype=np.int8)
+        message = payload if K_crc == 0 else attach_crc(payload, crc_poly)
+        tx = ldpc_rate_match(ldpc_encode(message[:k], H), E)
+        symbols = 1.0 - 2.0 * tx
+        noise = rng.normal(0.0, sg, size=symbols.shape)
+        llr = 2.0 * (symbols + noise) / nv
+        res = ldpc_decode_batch(ldpc_derate_match(llr, n), H, max_iter, alpha)
+        cand = res["hard"][0][: K_payload + K_crc]
+        be = int(np.count_nonzero(payload != cand[:K_payload]))
+        bits_total += K_payload
+        bit_errors += be
+        frame_errors += int(be > 0)
+        frames += 1
+        work += float(res["iters_used"][0])
+    return bits_total, bit_errors, frame_errors, frames, work

@@ -36,3 +36,8 @@ def gnr():
 @pytest.fixture(scope="session")
 def published():
     return json.loads((GOLDEN / "published.json").read_text())
+
+
+@pytest.fixture(scope="session")
+def gldpc():
+    return dict(np.load(GOLDEN / "ldpc.npz"))
