@@ -163,6 +163,60 @@ int pb200_channel_batch(pb200_engine *e, const pb200_sweep_cfg *cfg, uint8_t *d_
  * decode kernel that (M, forced) selects. */
 int pb200_kernel_info(pb200_engine *e, int M, int *warps_per_cta, int *ctas_per_sm, int *smem_bytes, int *regs);
 
+
+/* ==== NR LDPC (toy family of the comparison CLI) ===========================
+ * Reference: dl_scl_polar/nr/ldpc/{basegraphs,builder,encode,rate_match,decode_nms}.py and the nr_ldpc branch
+ * of eval/run_ber_sweep.py (:134-136,146-149,163-164,258-271).  One thread per frame, FLOAT64 arithmetic with
+ * the reference's operation order: hard decisions, iteration counts and posteriors are bit-identical to the
+ * reference's on the same float64 LLRs. */
+#define PB200_LDPC_MAX_N 4096
+
+typedef struct pb200_ldpc pb200_ldpc;
+
+/* basegraphs.py:39-42 load_base_graph + builder.py:20-30 build_h_matrix: dense H u8[3Z][6Z] on the HOST
+ * (h_H may be NULL to query the shape). */
+int pb200_ldpc_build_h(int bg, int Z, uint8_t *h_H, int *m, int *n);
+
+/* handle for one dense 0/1 parity-check matrix h_H[m][n] (host, row-major) */
+int pb200_ldpc_create(pb200_ldpc **out, int device, const uint8_t *h_H, int m, int n);
+void pb200_ldpc_destroy(pb200_ldpc *e);
+
+/* encode.py:52-66 encode_ldpc: payload[B,k] u8 -> code[B,n] u8 (systematic, parity by GF(2) elimination with free
+ * variables 0).  d_status: NULL or u8[B], 1 where the reference raises "Linear system over GF(2) has no solution". */
+int pb200_ldpc_encode_batch(pb200_ldpc *e, const uint8_t *d_payload, int k, uint8_t *d_code, uint8_t *d_status, int64_t B,
+                            void *stream);
+/* rate_match.py:8-15 rate_match_ldpc: code[B,N] -> out[B,E];  :18-38 derate_match_ldpc: llr[B,E] f64 -> out[B,N] f64 */
+int pb200_ldpc_rate_match_batch(const uint8_t *d_code, int N, int E, uint8_t *d_out, int64_t B, void *stream);
+int pb200_ldpc_derate_match_batch(const double *d_llr, int E, int N, double *d_out, int64_t B, void *stream);
+
+/* decode_nms.py:8-40 decode_ldpc_nms: llr[B,in_len] f64 (in_len = n, or E with the de-rate-matching fused into the
+ * load) -> hard[B,n] u8, posterior[B,n] f64, iters_used[B] i32, parity_ok[B] u8; any output may be NULL. */
+int pb200_ldpc_decode_batch(pb200_ldpc *e, const double *d_llr, int64_t B, int in_len, int max_iter, double alpha,
+                            int early_stop, uint8_t *d_hard, double *d_posterior, int32_t *d_iters, uint8_t *d_ok,
+                            void *stream);
+
+/* Fused Monte-Carlo sweep of run_ber_sweep.py:112-181 for --scheme nr_ldpc; Philox convention of pb200_sweep.
+ * counters (int64[PB200_NCOUNTERS], ADDED to): [0] frames [1] frame errors [2] payload bit errors [7] iterations. */
+typedef struct {
+    int k_payload;         /* payload bits                                                        */
+    int k_crc;             /* CRC bits appended (0 = none); k_payload + k_crc must equal n - m    */
+    int E;                 /* transmitted bits (rate_match_ldpc)                                  */
+    int max_iter;
+    int early_stop;
+    double alpha;
+    const char *crc_poly;  /* hex string incl. the leading 1; used when k_crc > 0                 */
+    double noise_var;
+    uint64_t seed;
+    uint32_t stream_id;
+    int64_t frame_begin;
+    int64_t n_frames;
+} pb200_ldpc_sweep_cfg;
+int pb200_ldpc_sweep(pb200_ldpc *e, const pb200_ldpc_sweep_cfg *cfg, int64_t *d_counters, uint8_t *d_frame_bit_errors,
+                     uint8_t *d_frame_work, void *stream);
+/* channel only, same Philox stream: payload[B,k_payload] u8 (NULL ok), llr[B,E] f64 */
+int pb200_ldpc_channel_batch(pb200_ldpc *e, const pb200_ldpc_sweep_cfg *cfg, uint8_t *d_payload, double *d_llr,
+                             void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,14 @@ class SweepCfg(C.Structure):
     ]
 
 
+class LdpcSweepCfg(C.Structure):
+    _fields_ = [
+        ("k_payload", C.c_int), ("k_crc", C.c_int), ("E", C.c_int), ("max_iter", C.c_int), ("early_stop", C.c_int),
+        ("alpha", C.c_double), ("crc_poly", C.c_char_p), ("noise_var", C.c_double), ("seed", C.c_uint64),
+        ("stream_id", C.c_uint32), ("frame_begin", _i64), ("n_frames", _i64),
+    ]
+
+
 # every symbol include/polar_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "pb200_last_error": (C.c_char_p, []),
@@ -57,6 +65,15 @@ SYMBOLS = {
     "pb200_sweep": (C.c_int, [_vp, C.POINTER(SweepCfg), _vp, _vp, _vp, _vp, _vp]),
     "pb200_channel_batch": (C.c_int, [_vp, C.POINTER(SweepCfg), _vp, _vp, _vp]),
     "pb200_kernel_info": (C.c_int, [_vp, C.c_int] + [C.POINTER(C.c_int)] * 4),
+    "pb200_ldpc_build_h": (C.c_int, [C.c_int, C.c_int, _vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "pb200_ldpc_create": (C.c_int, [C.POINTER(_vp), C.c_int, _vp, C.c_int, C.c_int]),
+    "pb200_ldpc_destroy": (None, [_vp]),
+    "pb200_ldpc_encode_batch": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _i64, _vp]),
+    "pb200_ldpc_rate_match_batch": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _i64, _vp]),
+    "pb200_ldpc_derate_match_batch": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _i64, _vp]),
+    "pb200_ldpc_decode_batch": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, C.c_double, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "pb200_ldpc_sweep": (C.c_int, [_vp, C.POINTER(LdpcSweepCfg), _vp, _vp, _vp, _vp]),
+    "pb200_ldpc_channel_batch": (C.c_int, [_vp, C.POINTER(LdpcSweepCfg), _vp, _vp, _vp]),
 }
 
 _lib = None

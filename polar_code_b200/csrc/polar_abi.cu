@@ -29,6 +29,7 @@ static int fail(int code, const char* fmt, ...) {
     g_err = buf;
     return code;
 }
+int pb200_set_error(int code, const char* msg) { g_err = msg; return code; }   // for the other ABI translation units
 #define CUDA_TRY(x)                                                                                   \
     do {                                                                                              \
         cudaError_t _e = (x);                                                                         \

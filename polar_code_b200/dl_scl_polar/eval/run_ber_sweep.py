@@ -1,9 +1,9 @@
-"""Unified payload-BER sweep CLI (polar_scl, dl_scl, nr_polar_scl) on the B200 engine.
+"""Unified payload-BER sweep CLI (polar_scl, dl_scl, nr_polar_scl, nr_ldpc) on the B200 engine.
 
 Same flags, row keys and CSV columns as the reference (dl_scl_polar/eval/run_ber_sweep.py:197-317).  The adaptive
 loop `while bit_errors < err_cap and bits_total < bits_cap` (:127) is reproduced exactly in global frame order on
-batched GPU chunks (polar_code_b200/montecarlo.py adaptive_cut).  `--scheme nr_ldpc` belongs to a different
-decoder family that is outside this engine's scope and raises NotImplementedError.
+batched GPU chunks (polar_code_b200/montecarlo.py adaptive_cut).  `--scheme nr_ldpc` (:258-271) runs the fused
+float64 LDPC sweep kernel of polar_code_b200/csrc/ldpc_kernels.cuh through the same adaptive loop.
 """
 
 from __future__ import annotations
@@ -105,10 +105,18 @@ def run(args: argparse.Namespace) -> List[Dict[str, float]]:
     seed_all(args.seed)
     N = args.N if args.N is not None else args.E
     K_total = args.K_payload + args.K_crc
-    if args.scheme == "nr_ldpc":
-        raise NotImplementedError("scheme nr_ldpc (layered NMS LDPC) is outside the polar engine's scope")
-    info_set = construct_info_set(N, K_total)
     beta, retries = None, -1
+    if args.scheme == "nr_ldpc":
+        from ..nr.ldpc import build_h_matrix, load_base_graph
+        from ..nr.ldpc._engines import ldpc_engine_for
+        H = build_h_matrix(load_base_graph(args.bg), args.Z)
+        if H.shape[1] - H.shape[0] != K_total:
+            raise ValueError("LDPC payload+CRC size mismatch with base graph")
+        eng = ldpc_engine_for(H)
+        eng.configure_sweep(k_crc=args.K_crc, E=args.E, max_iter=args.max_iter, alpha=args.alpha, crc_poly=args.crc_poly)
+        params_label = f"bg={args.bg},Z={args.Z},iter={args.max_iter},alpha={args.alpha}"
+        return _sweep_rows(args, eng, params_label, -1, None)
+    info_set = construct_info_set(N, K_total)
     if args.scheme == "polar_scl":
         if args.E != N:
             raise ValueError("polar_scl transmits the mother code: E must equal N")
@@ -120,7 +128,11 @@ def run(args: argparse.Namespace) -> List[Dict[str, float]]:
         eng, params_label, retries = engine_for(N, info_set, args.crc_poly), f"M={args.M},retries={args.retries}", args.retries
     else:
         eng, params_label = engine_for(N, info_set, args.crc_poly, E=args.E), f"M={args.M},ilv={args.ilv_mode}"
+    return _sweep_rows(args, eng, params_label, retries, beta)
 
+
+def _sweep_rows(args: argparse.Namespace, eng, params_label: str, retries: int, beta) -> List[Dict[str, float]]:
+    """The Eb/N0 loop of run_ber_sweep.py:275-291 over an engine that offers `sweep` (polar or LDPC)."""
     rows: List[Dict[str, float]] = []
     grid = np.arange(args.EbN0_lo, args.EbN0_hi + 1e-12, args.EbN0_step)
     for point, EbN0_dB in enumerate(grid):
@@ -128,7 +140,7 @@ def run(args: argparse.Namespace) -> List[Dict[str, float]]:
                           seed=args.seed, stream_id=point, err_cap=args.err_cap, bits_cap=args.bits_cap,
                           retries=retries, beta=beta)
         stats = SimulationStats(bits_total=st.frames * args.K_payload, bit_errors=st.bit_errors, frame_errors=st.frame_errors,
-                                work_sum=float(st.work_sum) if args.scheme == "dl_scl" else 0.0, frames=st.frames)
+                                work_sum=float(st.work_sum) if args.scheme in ("dl_scl", "nr_ldpc") else 0.0, frames=st.frames)
         row = stats.row()
         row.update({"scheme": args.scheme, "code": args.scheme, "N_or_E": args.E, "K_payload": args.K_payload,
                     "K_crc": args.K_crc, "rate": args.K_payload / args.E, "params": params_label, "EbN0_dB": float(EbN0_dB)})

@@ -210,3 +210,19 @@ def test_mirror_validation_without_gpu():
         retry_with_flip(np.zeros(128), A, 4, np.zeros(64, np.int8), 64)
     f = _force_vector(np.array([1, 0, 1, 1], np.int8), 2)
     assert list(f) == [1, 0, 0, -1]
+
+
+def test_ldpc_h_matrix_host_side(gldpc):
+    """pb200_ldpc_build_h is host code of the C-ABI: no GPU needed (basegraphs.py + builder.py)."""
+    from polar_code_b200.ldpc import build_h_matrix
+    from polar_code_b200.dl_scl_polar.nr.ldpc import load_base_graph
+    from polar_code_b200.dl_scl_polar.nr.ldpc.builder import build_h_matrix as mirror_build
+    for bg, Z in [(1, 2), (2, 2), (2, 4), (1, 8), (2, 32)]:
+        assert np.array_equal(build_h_matrix(bg, Z), gldpc[f"H_bg{bg}_Z{Z}"])
+        assert np.array_equal(mirror_build(load_base_graph(bg), Z), gldpc[f"H_bg{bg}_Z{Z}"])
+    g = load_base_graph(2)
+    assert (g.m, g.n) == (3, 6) and g.shifts[1, 2] == 3 and g.shifts[0, 4] == -1
+    with pytest.raises(ValueError):
+        load_base_graph(7)
+    with pytest.raises(ValueError):
+        build_h_matrix(2, 0)
