@@ -132,6 +132,8 @@ struct pb200_engine {
     int q_counts_n = 0;
     float* d_llr_store = nullptr;         // channel rows of frames in the DL-SCL retry queue (sweep mode)
     size_t llr_store_bytes = 0;
+    float* d_abs_store = nullptr;         // |L0| rows of frames in the DL-SCL retry queue
+    size_t abs_store_bytes = 0;
     // per-warp global scratch of the decode kernels, one buffer per stream: kernels of one engine that are
     // enqueued on different streams may overlap on the device and must not share tree rows
     std::map<cudaStream_t, std::pair<unsigned char*, size_t>> scratch;
@@ -244,7 +246,7 @@ extern "C" void pb200_destroy(pb200_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaFree(e->d_info_pos); cudaFree(e->d_info_mask); cudaFree(e->d_crc_tab); cudaFree(e->d_rm_src); cudaFree(e->d_tx_src); cudaFree(e->d_enc_tab);
-    cudaFree(e->d_llr_store); cudaFree(e->d_rm_dst);
+    cudaFree(e->d_llr_store); cudaFree(e->d_abs_store); cudaFree(e->d_rm_dst);
     for (auto& kv : e->scratch) cudaFree(kv.second.first); cudaFree(e->d_q[0]); cudaFree(e->d_q[1]); cudaFree(e->d_q_counts);
     for (int i = 0; i < 3; ++i) {
         if (e->hs[i]) cudaStreamDestroy(e->hs[i]);
@@ -297,18 +299,18 @@ static const void* pick_decode(int n, int MP, bool forced, bool metric) {
 static int round_mp(int M) { return M <= 1 ? 1 : M <= 2 ? 2 : M <= 4 ? 4 : 8; }
 
 // per-warp global scratch; sized for the smallest split (HS = 5) so every kernel of the engine fits
-static size_t warp_gbytes(int MP, int N) {
+static size_t warp_gbytes(int MP, int N, int K) {
     switch (MP) {
-        case 1: return WarpMem<1, 5>::gbytes(N);
-        case 2: return WarpMem<2, 5>::gbytes(N);
-        case 4: return WarpMem<4, 5>::gbytes(N);
-        default: return WarpMem<8, 5>::gbytes(N);
+        case 1: return WarpMem<1, 5>::gbytes(N, K);
+        case 2: return WarpMem<2, 5>::gbytes(N, K);
+        case 4: return WarpMem<4, 5>::gbytes(N, K);
+        default: return WarpMem<8, 5>::gbytes(N, K);
     }
 }
 
 // global scratch for `warps` resident warps of a launch on `st` (grows on demand; stays L2-resident across launches)
 static int ensure_scratch(pb200_engine* e, cudaStream_t st, size_t warps, int MP, unsigned char** out) {
-    const size_t need = warps * warp_gbytes(MP, e->code.N) + 256;
+    const size_t need = warps * warp_gbytes(MP, e->code.N, e->code.K) + 256;
     auto& slot = e->scratch[st];
     if (slot.second < need) {
         if (slot.first) {
@@ -323,21 +325,22 @@ static int ensure_scratch(pb200_engine* e, cudaStream_t st, size_t warps, int MP
     return PB200_OK;
 }
 
-// shared bytes per warp; round = DL-SCL retry kernel (HS = 5, holds the |L0| rows), otherwise the kernel's default split
-static size_t warp_bytes(int MP, int N, int xk, bool round = false) {
+// shared bytes per warp; xk > 0: the |L0| rows of the DL-SCL retry kernel, tk > 0: the lineage bytes of a trace-recording
+// kernel.  round = DL-SCL retry kernel (HS = 5), otherwise the kernel's default split
+static size_t warp_bytes(int MP, int N, int xk, bool round = false, int tk = 0) {
     if (round) {
         switch (MP) {
-            case 1: return WarpMem<1, 5>::bytes(N, xk);
-            case 2: return WarpMem<2, 5>::bytes(N, xk);
-            case 4: return WarpMem<4, 5>::bytes(N, xk);
-            default: return WarpMem<8, 5>::bytes(N, xk);
+            case 1: return WarpMem<1, 5>::bytes(N, xk, tk);
+            case 2: return WarpMem<2, 5>::bytes(N, xk, tk);
+            case 4: return WarpMem<4, 5>::bytes(N, xk, tk);
+            default: return WarpMem<8, 5>::bytes(N, xk, tk);
         }
     }
     switch (MP) {
-        case 1: return WarpMem<1>::bytes(N, xk);
-        case 2: return WarpMem<2>::bytes(N, xk);
-        case 4: return WarpMem<4>::bytes(N, xk);
-        default: return WarpMem<8>::bytes(N, xk);
+        case 1: return WarpMem<1>::bytes(N, xk, tk);
+        case 2: return WarpMem<2>::bytes(N, xk, tk);
+        case 4: return WarpMem<4>::bytes(N, xk, tk);
+        default: return WarpMem<8>::bytes(N, xk, tk);
     }
 }
 

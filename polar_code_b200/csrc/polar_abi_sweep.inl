@@ -21,6 +21,13 @@ static int ensure_queues(pb200_engine* e, long long frames, int retries, bool wa
         CUDA_TRY(cudaMalloc((void**)&e->d_llr_store, need_store));
         e->llr_store_bytes = need_store;
     }
+    const size_t need_abs = retries > 0 ? (size_t)frames * e->code.K * sizeof(float) : 0;
+    if (e->abs_store_bytes < need_abs) {
+        cudaFree(e->d_abs_store);
+        e->d_abs_store = nullptr; e->abs_store_bytes = 0;
+        CUDA_TRY(cudaMalloc((void**)&e->d_abs_store, need_abs));
+        e->abs_store_bytes = need_abs;
+    }
     if (e->q_bytes < need) {
         cudaFree(e->d_q[0]);
         e->d_q[0] = nullptr; e->q_bytes = 0;
@@ -75,14 +82,16 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
     const bool big = e->code.n > 7;
     Code code = e->code;
     code.M = M;
-    const void* base = big ? pb_sweep_kernel_9(MP, false) : pb_sweep_kernel_7(MP, false);
-    const void* round = big ? pb_sweep_kernel_9(MP, true) : pb_sweep_kernel_7(MP, true);
+    // with retries the baseline pass records the leaf-LLR trace and writes |L0| of every queued frame (kind 2)
+    const bool trace = a.retries > 0;
+    const void* base = big ? pb_sweep_kernel_9(MP, trace ? 2 : 0) : pb_sweep_kernel_7(MP, trace ? 2 : 0);
+    const void* round = big ? pb_sweep_kernel_9(MP, 1) : pb_sweep_kernel_7(MP, 1);
     KernelCfg kb, kr{};
-    int rc = choose_cfg(e, base, MP, 4, warp_bytes(MP, code.N, 0), &kb);
+    int rc = choose_cfg(e, base, MP, trace ? 6 : 4, warp_bytes(MP, code.N, 0, false, trace ? code.K : 0), &kb);
     if (rc) return rc;
     int rgrid = 0;
     if (a.retries > 0) {
-        rc = choose_cfg(e, round, MP, 5, warp_bytes(MP, code.N, code.K, true), &kr);
+        rc = choose_cfg(e, round, MP, 5, warp_bytes(MP, code.N, code.K, true, code.K), &kr);
         if (rc) return rc;
         rgrid = std::max(1, e->sms * kr.ctas_per_sm);
     }
@@ -112,6 +121,7 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
             rc = ensure_queues(e, nf, a.retries, a.llr == nullptr);
             if (rc) return rc;
             p.llr_store = (a.llr == nullptr) ? e->d_llr_store : nullptr;
+            p.abs_store = e->d_abs_store;
             CUDA_TRY(cudaMemsetAsync(e->d_q_counts, 0, sizeof(unsigned int) * (a.retries + 2), st));
             p.q_capacity = (unsigned int)nf;
             p.q_out = e->d_q[0];

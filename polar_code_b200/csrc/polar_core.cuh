@@ -126,24 +126,31 @@ struct WarpMem {
     float* scr;           // >= 3*max(N/32,1) lane-interleaved rows of scratch for the encoder / bit stash
     unsigned long long* xchg;  // [32][2] candidate keys for the rank exchange / small per-frame scratch (shared)
     float* absl;          // [FPW][xk+1] DL-SCL only: |L0| of the reference path (flip.py:102) (shared)
+    uint8_t* lin;         // [tk][32] trace mode only: slot a surviving path came from at info phase j (shared)
+    float* hist;          // [K][32] trace mode only: leaf LLR every slot saw at info phase j (global scratch)
     static constexpr int FPW = 32 / MP;
     __host__ __device__ static size_t tree_bytes(int N) { return (size_t)tree_rows_shared(N, HS) * 32 * 4; }
-    __host__ __device__ static size_t bytes(int N, int xk = 0) {          // shared bytes per warp
+    // shared bytes per warp: xk > 0 adds the |L0| rows, tk > 0 the lineage bytes of the trace (info_llrs without a replay)
+    __host__ __device__ static size_t bytes(int N, int xk = 0, int tk = 0) {
         size_t x = xk ? (((size_t)FPW * (xk + 1) * 4 + 15) & ~(size_t)15) : 0;
-        return tree_bytes(N) + kXchgBytes + x;
+        size_t t = (tk && MP > 1) ? (size_t)tk * 32 : 0;
+        return tree_bytes(N) + kXchgBytes + x + t;
     }
-    __host__ __device__ static size_t gbytes(int N) {                     // global scratch bytes per warp
+    __host__ __device__ static size_t gbytes(int N, int K) {              // global scratch bytes per warp
         size_t t = (size_t)tree_rows_global(N, HS) * 32 * 4;
         size_t ch = (((size_t)FPW * chan_stride(N) * 4) + 127) & ~(size_t)127;
-        return t + ch;
+        return t + ch + (size_t)K * 32 * 4;
     }
-    __device__ void carve(unsigned char* sbase, unsigned char* gbase, int N) {
+    __device__ void carve(unsigned char* sbase, unsigned char* gbase, int N, int xk = 0) {
         ts = reinterpret_cast<float*>(sbase);
         xchg = reinterpret_cast<unsigned long long*>(sbase + tree_bytes(N));
         absl = reinterpret_cast<float*>(sbase + tree_bytes(N) + kXchgBytes);
+        lin = sbase + bytes(N, xk, 0);
         float* g = reinterpret_cast<float*>(gbase);
         tg = g - ((1 << HS) - 2) * 32;
         chan = g + (size_t)tree_rows_global(N, HS) * 32;
+        hist = reinterpret_cast<float*>(gbase + (size_t)tree_rows_global(N, HS) * 32 * 4 +
+                                        ((((size_t)FPW * chan_stride(N) * 4) + 127) & ~(size_t)127));
         const int need = 3 * (N >= 32 ? N / 32 : 1);
         scr = (tree_rows_shared(N, HS) >= need) ? ts : g;
     }

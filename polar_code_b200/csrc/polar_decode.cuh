@@ -94,6 +94,10 @@ struct ListDecoder {
     // Decode the FPW frames of this warp; `chanf` = this lane's frame's channel row (N floats, stride 1).
     // fmask/fval (FORCED): per-frame masks over phases -- bit phi of fmask set <=> u_phi is forced to bit phi of
     // fval (scl.py:138-144,155-161).
+    // TRACE: also record, per information phase j, the leaf LLR every slot saw (wm.hist[j][lane]) and the slot each
+    // surviving path came from (wm.lin[j][lane]); trace_walk() then yields a path's info_llrs (scl.py:159,167)
+    // without the SC replay.
+    template <bool TRACE = false>
     static __device__ __forceinline__ void run(const Code& code, const uint32_t* __restrict__ imask, const WM& wm, PathT& p,
                                                int lane, const float* chanf, const uint32_t (&fmask)[XW],
                                                const uint32_t (&fval)[XW], uint32_t& flags) {
@@ -104,6 +108,7 @@ struct ListDecoder {
         uint32_t tie = 0;
         uint32_t cur_info = 0, cur_fm = 0, cur_fv = 0;   // word phi/32 of the info / force masks
         float a = 0.f, b = 0.f;                          // height-1 pair of the current phase pair
+        int jinfo = 0;                                   // index of the current information phase (TRACE)
         for (int phi = 0; phi < N; ++phi) {
             if ((phi & 31) == 0) {
                 cur_info = __ldg(imask + (phi >> 5));     // (a dynamic index into the by-value Code would force it into local memory)
@@ -135,6 +140,7 @@ struct ListDecoder {
                     a1 = a1 && (forced_val == 1);
                 }
                 if constexpr (MP == 1) {
+                    if constexpr (TRACE) { if (is_info) { wm.hist[jinfo * 32 + lane] = L; ++jinfo; } }
                     const double m1 = p.m + ((double)fmaxf(L, 0.f) + dtail);       // bit 1: logaddexp(0, L)
                     bool pick1 = a1 && (!a0 || m1 < m0);
                     if (a0 && a1) {
@@ -190,6 +196,11 @@ struct ListDecoder {
                             for (int i = 0; i < MP / 2; ++i) if (i < k) d &= d - 1;
                             if (d) { src = gbase + __ffs(d) - 1; take = true; }
                         }
+                        if constexpr (TRACE) {
+                            wm.hist[jinfo * 32 + lane] = L;
+                            wm.lin[jinfo * 32 + lane] = (uint8_t)(src - gbase);
+                            ++jinfo;
+                        }
                         // The second child of a doubly-surviving path moves into a freed slot.  Every lane reads from
                         // `src`; lanes that take no clone have src == lane, so what they read back is their own state
                         // and the assignments below need no select.
@@ -242,6 +253,20 @@ struct ListDecoder {
             __syncwarp();
         }
         if (tie) flags |= PB_FLAG_NEAR_TIE;
+    }
+
+    // info_llrs of the path that ended in lane `end_lane` (group-uniform), from the trace of a run<true>():
+    // sink(j, L) is called on the group lane with slot == j mod MP.
+    template <typename Sink>
+    static __device__ __forceinline__ void trace_walk(const Code& code, const WM& wm, int lane, int end_lane, Sink&& sink) {
+        const int slot = lane & (MP - 1), gbase = lane & ~(MP - 1);
+        int s = end_lane & (MP - 1);
+        for (int j = code.K - 1; j >= 0; --j) {
+            int w = 0;
+            if constexpr (MP > 1) w = wm.lin[j * 32 + gbase + s];
+            if ((j & (MP - 1)) == slot) sink(j, wm.hist[j * 32 + gbase + w]);
+            s = w;
+        }
     }
 
     // SC pass along the known bits `u` (own slot only), reporting the leaf LLR of every information phase:

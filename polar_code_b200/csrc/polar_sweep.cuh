@@ -85,6 +85,7 @@ struct SweepArgs {
     unsigned int* q_out_count;
     unsigned int q_capacity;
     float* llr_store;              // [q_capacity][N] channel rows of the frames that entered the retry queue (Philox mode)
+    float* abs_store;              // [q_capacity][K] |L0| of the baseline best path of every queued frame (flip.py:102)
     unsigned char* gscratch;       // per-warp global scratch (WarpMem::gbytes each)
 };
 
@@ -295,7 +296,7 @@ struct Sweep {
     static constexpr uint32_t GM = DecU::GM;
     using Entry = DlEntry<XW>;
 
-    struct Best { uint32_t u[XW]; bool pass; uint32_t flags; };   // identical on all lanes of a group
+    struct Best { uint32_t u[XW]; bool pass; uint32_t flags; int lane; };   // identical on all lanes of a group
 
     // best candidate of a finished list decode (scl.py:183-197), broadcast to the group
     static __device__ __forceinline__ void pick_best(const Code& code, const Tables& tb, const PathT& p, int lane, uint32_t flags, Best& b) {
@@ -314,6 +315,7 @@ struct Sweep {
 #pragma unroll
         for (int k = 0; k < XW; ++k) b.u[k] = __shfl_sync(kFull, u[k], bl);
         b.pass = __shfl_sync(kFull, (int)pass, bl) != 0;
+        b.lane = bl;
 #pragma unroll
         for (int o = 1; o < MP; o <<= 1) flags |= __shfl_xor_sync(kFull, flags, o);
         b.flags = flags;
@@ -364,11 +366,12 @@ struct Sweep {
 
     // Warp-aggregated append of the leaders with `need` to the output queue.  `store` < 0: first time this frame is
     // queued -> its channel row (chanf, N floats) is copied to llr_store[slot] and slot becomes its store index.
-    static __device__ __forceinline__ void enqueue(const Code& code, const SweepArgs& a, int lane, bool need, long long frame, const Best& b,
-                                                   const uint32_t (&tried)[XW], uint32_t n_tried, const uint32_t (&u_sent)[XW],
-                                                   long long store, const float* chanf) {
+    // Returns the queue slot of this lane's entry (-1: none).
+    static __device__ __forceinline__ long long enqueue(const Code& code, const SweepArgs& a, int lane, bool need, long long frame, const Best& b,
+                                                        const uint32_t (&tried)[XW], uint32_t n_tried, const uint32_t (&u_sent)[XW],
+                                                        long long store, const float* chanf) {
         const uint32_t m = __ballot_sync(kFull, need);
-        if (m == 0) return;
+        if (m == 0) return -1;
         unsigned int base = 0;
         if (lane == 0) base = atomicAdd(a.q_out_count, (unsigned int)__popc(m));
         base = __shfl_sync(kFull, base, 0);
@@ -393,6 +396,7 @@ struct Sweep {
                 for (int i = lane & (MP - 1); i < code.N; i += MP) dst[i] = chanf[i];
             }
         }
+        return slot;
     }
 
     static __device__ __forceinline__ void flush(const SweepArgs& a, int lane, uint32_t (&acc)[cNum]) {
@@ -408,7 +412,9 @@ struct Sweep {
 // ---------------------------------------------------------------------------------------------------
 // Baseline pass: channel -> SCL(M) -> counters; failing frames go to the retry queue.
 // ---------------------------------------------------------------------------------------------------
-template <int MP, int LOGMAX, int HS = DefaultHS<MP>::value>
+// TRACE (chosen when DL-SCL retries follow): the list decode records the leaf-LLR trace, and every frame that enters
+// the retry queue gets the |L0| vector of its best path written to abs_store (no SC replay anywhere in DL-SCL).
+template <int MP, int LOGMAX, bool TRACE = false, int HS = DefaultHS<MP>::value>
 __global__ void __launch_bounds__(768) sweep_kernel(const Code code, const Tables tb, const SweepArgs a) {
     using S = Sweep<MP, LOGMAX, HS>;
     using WM = WarpMem<MP, HS>;
@@ -417,7 +423,8 @@ __global__ void __launch_bounds__(768) sweep_kernel(const Code code, const Table
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     WM wm;
-    wm.carve(smem + (size_t)warp * WM::bytes(code.N), a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WM::gbytes(code.N), code.N);
+    wm.carve(smem + (size_t)warp * WM::bytes(code.N, 0, TRACE ? code.K : 0),
+             a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WM::gbytes(code.N, code.K), code.N);
     const bool leader = (lane & (MP - 1)) == 0;
     uint32_t acc[cNum];
 #pragma unroll
@@ -441,7 +448,7 @@ __global__ void __launch_bounds__(768) sweep_kernel(const Code code, const Table
         PathT p;
         S::DecU::init(p, lane, valid);
         const float* chanf = wm.chan + (lane / MP) * chan_stride(code.N);
-        S::DecU::run(code, tb.info_mask, wm, p, lane, chanf, fm, fv, flags);
+        S::DecU::template run<TRACE>(code, tb.info_mask, wm, p, lane, chanf, fm, fv, flags);
         typename S::Best b;
         S::pick_best(code, tb, p, lane, flags, b);
         bool need = false;
@@ -472,7 +479,15 @@ __global__ void __launch_bounds__(768) sweep_kernel(const Code code, const Table
         }
         if (a.retries >= 0) {
             if (leader && valid && !need) S::finish_dl(code, tb, a, wm, lane, my_frame, b, 0, u_sent, acc);
-            S::enqueue(code, a, lane, need, my_frame, b, tried, 0, u_sent, -1, chanf);
+            long long qslot = S::enqueue(code, a, lane, need, my_frame, b, tried, 0, u_sent, -1, chanf);
+            if constexpr (TRACE) {
+                // |L0| of the best path of a queued frame (flip.py:102), straight from the trace
+                qslot = __shfl_sync(kFull, qslot, lane & ~(MP - 1));
+                if (qslot >= 0) {
+                    float* dst = a.abs_store + qslot * (long long)code.K;
+                    S::DecU::trace_walk(code, wm, lane, b.lane, [&](int j, float L) { dst[j] = fabsf(L); });
+                }
+            }
         }
         __syncwarp();
     }
@@ -484,8 +499,10 @@ __global__ void __launch_bounds__(768) sweep_kernel(const Code code, const Table
 // Every lane group owns one frame at a time and keeps it through all of its retries (reference bits, tried set,
 // flags live in registers); a group whose frame is finished pulls the next queue entry (warp-aggregated atomic),
 // so all lanes stay busy until the queue is drained and there are no per-round launches or queue round trips.
-// Per retry: replay the reference path for |L0| (flip.py:102,133), rank q = |L0| @ beta in fp64 (flip.py:104-108),
-// force prefix + flipped bit (flip.py:30-34), list-decode (flip.py:53), then finish or go on (flip.py:127-135).
+// Per retry: rank q = |L0| @ beta in fp64 (flip.py:104-108), force prefix + flipped bit (flip.py:30-34), list-decode
+// (flip.py:53), then finish or go on (flip.py:127-135).  |L0| of the reference path (flip.py:102,133) comes from the
+// trace the previous list decode of that frame left behind (baseline: abs_store; retries: trace_walk) -- the leaf
+// LLRs are never recomputed by an SC replay.
 // ---------------------------------------------------------------------------------------------------
 template <int MP, int LOGMAX, int HS = 5>
 __global__ void __launch_bounds__(640) dl_retry_kernel(const Code code, const Tables tb, const SweepArgs a) {
@@ -497,8 +514,10 @@ __global__ void __launch_bounds__(640) dl_retry_kernel(const Code code, const Ta
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     WM wm;
-    wm.carve(smem + (size_t)warp * WM::bytes(code.N, code.K), a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WM::gbytes(code.N), code.N);
+    wm.carve(smem + (size_t)warp * WM::bytes(code.N, code.K, code.K),
+             a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WM::gbytes(code.N, code.K), code.N, code.K);
     const int slot = lane & (MP - 1), fme = lane / MP, gbase = lane & ~(MP - 1);
+    float* ab = wm.absl + fme * (code.K + 1);      // |L0| of the reference path of this group's frame
     const bool leader = slot == 0;
     const int K = code.K;
     uint32_t acc[cNum];
@@ -532,8 +551,11 @@ __global__ void __launch_bounds__(640) dl_retry_kernel(const Code code, const Ta
 #pragma unroll
                         for (int k = 0; k < XW; ++k) { u_ref[k] = e->u[k]; tried[k] = e->tried[k]; u_sent[k] = e->u_sent[k]; }
                         active = true;
+                        const float* src = a.abs_store + store * (long long)K;     // written by the baseline pass
+                        for (int j = slot; j < K; j += MP) ab[j] = src[j];
                     } else exhausted = true;
                 }
+                __syncwarp();
             }
         }
         if (!__any_sync(kFull, active)) break;
@@ -547,10 +569,6 @@ __global__ void __launch_bounds__(640) dl_retry_kernel(const Code code, const Ta
             load_channel_ids<MP, WM>(code, tb, wm, a.llr, a.in_len, valid ? my_frame : -1, a.frame_begin, lane);
             chanf = wm.chan + fme * chan_stride(code.N);
         }
-        // |L0| of the reference path (flip.py:102,133): replay it and keep the info-phase leaf LLRs
-        float* ab = wm.absl + fme * (K + 1);
-        S::DecU::replay(code, tb.info_mask, wm, lane, valid, chanf, u_ref, [&](int j, float L) { if (leader) ab[j] = fabsf(L); });
-        __syncwarp();
         // rank_indices (flip.py:104-108): first untried index of argsort(|L0| @ beta) = argmin over untried
         double m1 = 1e300, m2 = 1e300;
         int a1 = 0x7fffffff;
@@ -612,7 +630,7 @@ __global__ void __launch_bounds__(640) dl_retry_kernel(const Code code, const Ta
         uint32_t flags = 0;
         PathT p;
         S::DecF::init(p, lane, valid);
-        S::DecF::run(code, tb.info_mask, wm, p, lane, chanf, fm, fv, flags); // retry_with_flip (flip.py:37-62)
+        S::DecF::template run<true>(code, tb.info_mask, wm, p, lane, chanf, fm, fv, flags); // retry_with_flip (flip.py:37-62)
         typename S::Best b;
         S::pick_best(code, tb, p, lane, flags | eflags, b);
         if (valid) {
@@ -627,6 +645,7 @@ __global__ void __launch_bounds__(640) dl_retry_kernel(const Code code, const Ta
                 eflags = b.flags;
 #pragma unroll
                 for (int k = 0; k < XW; ++k) u_ref[k] = b.u[k];
+                S::DecF::trace_walk(code, wm, lane, b.lane, [&](int j, float L) { ab[j] = fabsf(L); });   // flip.py:133
             }
         }
         __syncwarp();
@@ -643,7 +662,7 @@ __global__ void channel_kernel(const Code code, const Tables tb, const SweepArgs
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     using WM = WarpMem<MP, 5>;
     WM wm;
-    wm.carve(smem + (size_t)warp * WM::bytes(code.N), a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WM::gbytes(code.N), code.N);
+    wm.carve(smem + (size_t)warp * WM::bytes(code.N), a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WM::gbytes(code.N, code.K), code.N);
     const long long ngroups = (a.n_frames + FPW - 1) / FPW;
     for (long long g = (long long)blockIdx.x * wpc + warp; g < ngroups; g += (long long)gridDim.x * wpc) {
         const long long idx = g * FPW + lane / MP;

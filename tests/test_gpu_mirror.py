@@ -179,9 +179,9 @@ def test_ber_sweep_small_configs(tmp_path):
             "--plot", str(tmp_path / "c.png")] + common)
     txt = (tmp_path / "c.csv").read_text().splitlines()
     assert txt[0] == ",".join(R.HEADER) and len(txt) == 4 and (tmp_path / "c.png").exists()
-    with pytest.raises(NotImplementedError):
-        R.run(R.parse_args(["--scheme", "nr_ldpc", "--K_payload", "6", "--K_crc", "0", "--E", "12", "--EbN0_lo", "5",
-                            "--EbN0_hi", "5", "--out", str(tmp_path / "d.csv")]))
+    rows = R.run(R.parse_args(["--scheme", "nr_ldpc", "--K_payload", "6", "--K_crc", "0", "--E", "12", "--EbN0_lo", "5",
+                               "--EbN0_hi", "5", "--bits_cap", "600", "--out", str(tmp_path / "d.csv")]))
+    assert rows[0]["scheme"] == "nr_ldpc" and rows[0]["bits_total"] % 6 == 0 and rows[0]["avg_work"] >= 1.0
 
 
 def test_ber_sweep_stop_rule_is_the_sequential_loop(tmp_path):
