@@ -114,7 +114,7 @@ struct pb200_engine {
     uint32_t* d_crc_tab = nullptr;
     int16_t* d_rm_src = nullptr;
     int16_t* d_tx_src = nullptr;   // NR transmit gather: tx[e] = code[tx_src[e]] or pad (-1)
-    uint32_t* d_enc_tab = nullptr; // sweep encoder tables
+    std::map<int, uint32_t*> enc_tabs;   // sweep encoder tables, one per payload length (polar_abi_sweep.inl get_enc_tab)
     std::map<std::tuple<int, int, int>, KernelCfg> cfg_cache;
     // host-buffer pipeline
     cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
@@ -245,7 +245,8 @@ extern "C" int pb200_create(pb200_engine** out, int device, int N, const int32_t
 extern "C" void pb200_destroy(pb200_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
-    cudaFree(e->d_info_pos); cudaFree(e->d_info_mask); cudaFree(e->d_crc_tab); cudaFree(e->d_rm_src); cudaFree(e->d_tx_src); cudaFree(e->d_enc_tab);
+    cudaFree(e->d_info_pos); cudaFree(e->d_info_mask); cudaFree(e->d_crc_tab); cudaFree(e->d_rm_src); cudaFree(e->d_tx_src);
+    for (auto& kv : e->enc_tabs) cudaFree(kv.second);
     cudaFree(e->d_llr_store); cudaFree(e->d_abs_store); cudaFree(e->d_rm_dst);
     for (auto& kv : e->scratch) cudaFree(kv.second.first); cudaFree(e->d_q[0]); cudaFree(e->d_q[1]); cudaFree(e->d_q_counts);
     for (int i = 0; i < 3; ++i) {

@@ -43,7 +43,39 @@ static int ensure_queues(pb200_engine* e, long long frames, int retries, bool wa
     return PB200_OK;
 }
 
-static void fill_chan(pb200_engine* e, const pb200_sweep_cfg* c, ChanCfg* cc) {
+// Encoder table of the sweep for payload length kp: row (q, v) = the u word (XW u32) produced by payload nibble q
+// holding value v -- its bits at their information positions (polar.py:116-117) plus, when CRC bits follow the
+// payload, their contribution to each CRC bit (crc.py:19-37 is linear with a zero initial register).
+static int get_enc_tab(pb200_engine* e, int kp, const uint32_t** out) {
+    auto it = e->enc_tabs.find(kp);
+    if (it != e->enc_tabs.end()) { *out = it->second; return PB200_OK; }
+    const int K = e->code.K, deg = e->code.crc_deg, XWk = e->code.n <= 7 ? 4 : 16;
+    const int nq = (kp + 3) / 4;
+    std::vector<uint32_t> tab((size_t)nq * 16 * XWk, 0);
+    std::vector<std::vector<uint32_t>> bitrow(kp, std::vector<uint32_t>(XWk, 0));   // u contribution of payload bit j
+    for (int j = 0; j < kp; ++j) {
+        auto put = [&](int msg_index) { const int pos = e->info_pos[msg_index]; bitrow[j][pos >> 5] ^= 1u << (pos & 31); };
+        put(j);
+        if (kp < K && deg > 0) {
+            const unsigned long long rem = xpow_mod(kp - 1 - j + deg, e->poly, deg);   // remainder of x^(kp-1-j) * x^deg
+            for (int t = 0; t < deg && kp + t < K; ++t)
+                if ((rem >> (deg - 1 - t)) & 1ull) put(kp + t);
+        }
+    }
+    for (int q = 0; q < nq; ++q)
+        for (int v = 0; v < 16; ++v)
+            for (int b = 0; b < 4; ++b)
+                if (((v >> b) & 1) && q * 4 + b < kp)
+                    for (int w = 0; w < XWk; ++w) tab[((size_t)q * 16 + v) * XWk + w] ^= bitrow[q * 4 + b][w];
+    uint32_t* d = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d, tab.size() * 4));
+    CUDA_TRY(cudaMemcpy(d, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    e->enc_tabs[kp] = d;
+    *out = d;
+    return PB200_OK;
+}
+
+static int fill_chan(pb200_engine* e, const pb200_sweep_cfg* c, ChanCfg* cc) {
     cc->k0 = (uint32_t)(c->seed & 0xffffffffu);
     cc->k1 = (uint32_t)(c->seed >> 32) + 0x9E3779B9u * c->stream_id;
     cc->sigma = (float)sqrt(c->noise_var);
@@ -57,6 +89,7 @@ static void fill_chan(pb200_engine* e, const pb200_sweep_cfg* c, ChanCfg* cc) {
     cc->deg = e->code.crc_deg;
     cc->tx_src = e->d_tx_src;
     cc->rm_dst = e->d_rm_dst;
+    return get_enc_tab(e, c->k_payload, &cc->enc_tab);
 }
 
 static int check_sweep_cfg(pb200_engine* e, const pb200_sweep_cfg* c) {
@@ -87,11 +120,11 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
     const void* base = big ? pb_sweep_kernel_9(MP, trace ? 2 : 0) : pb_sweep_kernel_7(MP, trace ? 2 : 0);
     const void* round = big ? pb_sweep_kernel_9(MP, 1) : pb_sweep_kernel_7(MP, 1);
     KernelCfg kb, kr{};
-    int rc = choose_cfg(e, base, MP, trace ? 6 : 4, warp_bytes(MP, code.N, 0, false, trace ? code.K : 0), &kb);
+    int rc = choose_cfg(e, base, MP, trace ? 6 : 4, warp_bytes(MP, code.N, 0, false, trace ? code.K : 0) + kAccBytes, &kb);
     if (rc) return rc;
     int rgrid = 0;
     if (a.retries > 0) {
-        rc = choose_cfg(e, round, MP, 5, warp_bytes(MP, code.N, code.K, true, code.K), &kr);
+        rc = choose_cfg(e, round, MP, 5, warp_bytes(MP, code.N, code.K, true, code.K) + kAccBytes, &kr);
         if (rc) return rc;
         rgrid = std::max(1, e->sms * kr.ctas_per_sm);
     }
@@ -174,7 +207,8 @@ extern "C" int pb200_sweep(pb200_engine* e, const pb200_sweep_cfg* c, const floa
     SweepArgs a{};
     a.llr = nullptr; a.in_len = 0;
     a.frame_begin = c->frame_begin; a.n_frames = c->n_frames;
-    fill_chan(e, c, &a.cc);
+    rc = fill_chan(e, c, &a.cc);
+    if (rc) return rc;
     a.retries = c->retries; a.run_scl = c->run_scl; a.fe_mode = c->frame_error_mode;
     span_mask(e, c->bit_error_span, a.be_mask);
     a.beta = d_beta;
@@ -214,7 +248,8 @@ extern "C" int pb200_channel_batch(pb200_engine* e, const pb200_sweep_cfg* c, ui
     CUDA_TRY(cudaSetDevice(e->device));
     SweepArgs a{};
     a.frame_begin = c->frame_begin; a.n_frames = c->n_frames;
-    fill_chan(e, c, &a.cc);
+    rc = fill_chan(e, c, &a.cc);
+    if (rc) return rc;
     a.cc.include_uncoded = 0;
     const size_t wb = WarpMem<4, 5>::bytes(e->code.N);
     const int wpc = 4;
@@ -256,7 +291,8 @@ extern "C" int pb200_nr_encode_batch(pb200_engine* e, const uint8_t* payload, in
     c.noise_var = 1.0; c.noise_var_uncoded = 1.0;
     c.k_payload = e->code.K - e->code.crc_deg;
     ChanCfg cc;
-    fill_chan(e, &c, &cc);
+    int rc = fill_chan(e, &c, &cc);
+    if (rc) return rc;
     nr_encode_kernel<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(e->code, e->tb, cc, payload, tx, B, E);
     CUDA_TRY(cudaGetLastError());
     return PB200_OK;

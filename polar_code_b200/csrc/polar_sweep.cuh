@@ -52,6 +52,7 @@ struct ChanCfg {
     int include_uncoded;
     unsigned long long poly;   // CRC polynomial incl. leading 1
     int deg;
+    const uint32_t* enc_tab;   // [ceil(kp/4)][16][XW] u-word contribution of payload nibble q with value v (CRC bits included)
     const int16_t* tx_src;     // [E] NR transmit gather (code index or -1 = pad symbol +3)
     const int16_t* rm_dst;     // [N] NR: internal index fed by de-rate-matched position p (-1 none)
 };
@@ -94,6 +95,14 @@ struct SweepArgs {
 template <int XW> struct DlEntry { DlEntryHdr h; uint32_t u[XW]; uint32_t tried[XW]; uint32_t u_sent[XW]; uint32_t store; uint32_t pad; };
 
 // counters indices (include/polar_b200.h)
+// Per-lane counter column in shared memory (c-th counter of this lane at p[c*32]): keeps the 12 running totals out of
+// the register file of the persistent kernels; flush() reduces them over the warp and adds them to the global block.
+struct AccRef {
+    uint32_t* p;
+    __device__ __forceinline__ uint32_t& operator[](int c) const { return p[c * 32]; }
+};
+constexpr int kAccBytes = 12 * 32 * 4;
+
 enum { cFrames = 0, cSclFe, cSclBe, cDlFe, cDlBe, cUncFe, cUncBe, cDlWork, cNearTie, cSclUndet, cDlUndet, cRankTie, cNum };
 
 // ---------------------------------------------------------------------------------------------------
@@ -101,71 +110,79 @@ enum { cFrames = 0, cSclFe, cSclBe, cDlFe, cDlBe, cUncFe, cUncBe, cDlWork, cNear
 // Leaves the channel LLRs in wm.chan, returns the transmitted u (all lanes of the group) and the frame's uncoded
 // bit-error count.  Scratch: the (not yet used) tree area.
 // ---------------------------------------------------------------------------------------------------
+#ifndef PB_RETRY_THREADS
+#define PB_RETRY_THREADS 640
+#endif
+#ifndef PB_SWEEP_THREADS
+#define PB_SWEEP_THREADS 1024
+#endif
 template <int MP, int XW, typename WM>
 __device__ __forceinline__ void gen_channel(const Code& code, const Tables& tb, const ChanCfg& cc, const WM& wm,
                                             long long my_frame, int lane, uint32_t (&u_sent)[XW], uint32_t& unc_err,
                                             bool want_chan, float* raw_out = nullptr, long long raw_base = 0) {
     constexpr int FPW = 32 / MP;
-    const int N = code.N, K = code.K;
+    const int N = code.N;
     const int xwn = N >= 32 ? N / 32 : 1;
-    const int slot = lane & (MP - 1), gbase = lane & ~(MP - 1), fme = lane / MP;
+    const int slot = lane & (MP - 1), fme = lane / MP;
     uint32_t* scr = reinterpret_cast<uint32_t*>(wm.scr);       // per-lane column: scr[w*32 + lane]
     const uint2 key = make_uint2(cc.k0, cc.k1);
     const int pwn = (cc.kp + 31) / 32;
-    // ---- payload -> CRC -> u -> x on the group leader ------------------------------------------------
-    // scratch rows of the leader's column: payload [0,xwn), message [xwn,2xwn), u / codeword [2xwn,3xwn)
-    const int R1 = xwn, R2 = 2 * xwn;
-    if (slot == 0 && my_frame >= 0) {
-        for (int w = 0; w < xwn; ++w) { scr[w * 32 + lane] = 0; scr[(R1 + w) * 32 + lane] = 0; scr[(R2 + w) * 32 + lane] = 0; }
-        for (int w = 0; w < pwn; w += 4) {
-            const uint4 r = philox4x32_10(make_uint4((uint32_t)my_frame, (uint32_t)(my_frame >> 32), (uint32_t)(w >> 2), kPurposePayload), key);
-            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+    // ---- payload -> CRC -> u, on every lane of the group (no staging): the payload words come from Philox and
+    // u = XOR over the payload nibbles of one row of the encoder table (payload bits at their information positions
+    // plus their linear contribution to the CRC bits, crc.py:19-37 + polar.py:116-117)
+    const int R2 = 2 * xwn;                                    // scratch rows: payload [0,xwn), codeword [2xwn,3xwn)
+    uint32_t pw[XW];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                if (w + c < pwn) {
-                    uint32_t v = rr[c];
-                    const int rem = cc.kp - (w + c) * 32;
-                    if (rem < 32) v &= (1u << rem) - 1u;
-                    scr[(w + c) * 32 + lane] = v;
-                    scr[(R1 + w + c) * 32 + lane] = v;
+    for (int w = 0; w < XW; ++w) { pw[w] = 0; u_sent[w] = 0; }
+    if (my_frame >= 0) {
+#pragma unroll
+        for (int w4 = 0; w4 < XW; w4 += 4) {
+            if (w4 < pwn) {
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)my_frame, (uint32_t)(my_frame >> 32), (uint32_t)(w4 >> 2), kPurposePayload), key);
+                const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (w4 + c < XW && w4 + c < pwn) {
+                        uint32_t v = rr[c];
+                        const int rem = cc.kp - (w4 + c) * 32;
+                        if (rem < 32) v &= (1u << rem) - 1u;
+                        pw[w4 + c] = v;
+                    }
                 }
             }
         }
-        // attach_crc (crc.py:19-37): remainder of payload(x) x^deg, appended MSB first
-        if (cc.kp < K) {
-            const unsigned long long low = cc.poly & ((1ull << cc.deg) - 1ull);
-            unsigned long long reg = 0;
-            for (int j = 0; j < cc.kp; ++j) {
-                const unsigned long long b = (scr[(j >> 5) * 32 + lane] >> (j & 31)) & 1u;
-                const unsigned long long top = ((reg >> (cc.deg - 1)) & 1ull) ^ b;
-                reg = (reg << 1) & ((1ull << cc.deg) - 1ull);
-                if (top) reg ^= low;
+        const int nq = (cc.kp + 3) >> 2;
+#pragma unroll
+        for (int w = 0; w < XW; ++w) {
+            if (w < pwn) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int q = w * 8 + k;
+                    if (q < nq) {
+                        const uint32_t* row = cc.enc_tab + ((size_t)q * 16 + ((pw[w] >> (4 * k)) & 15u)) * XW;
+                        if constexpr (XW % 4 == 0) {
+#pragma unroll
+                            for (int x4 = 0; x4 < XW; x4 += 4) {
+                                const uint4 t = __ldg(reinterpret_cast<const uint4*>(row + x4));
+                                u_sent[x4] ^= t.x; u_sent[x4 + 1] ^= t.y; u_sent[x4 + 2] ^= t.z; u_sent[x4 + 3] ^= t.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int x = 0; x < XW; ++x) u_sent[x] ^= __ldg(row + x);
+                        }
+                    }
+                }
             }
-            for (int t = 0; t < cc.deg && cc.kp + t < K; ++t) {
-                const int j = cc.kp + t;
-                const uint32_t b = (uint32_t)((reg >> (cc.deg - 1 - t)) & 1ull);
-                scr[(R1 + (j >> 5)) * 32 + lane] |= b << (j & 31);
-            }
-        }
-        // u[A] = msg (polar.py:116-117)
-        for (int j = 0; j < K; ++j) {
-            const uint32_t b = (scr[(R1 + (j >> 5)) * 32 + lane] >> (j & 31)) & 1u;
-            const int pos = __ldg(&tb.info_pos[j]);
-            scr[(R2 + (pos >> 5)) * 32 + lane] |= b << (pos & 31);
         }
     }
-    __syncwarp();
-#pragma unroll
-    for (int w = 0; w < XW; ++w) u_sent[w] = (w < xwn) ? scr[(R2 + w) * 32 + gbase] : 0u;
     uint32_t x[XW];
 #pragma unroll
     for (int w = 0; w < XW; ++w) x[w] = u_sent[w];
     transform_words<XW>(x, code.n);                           // codeword (polar.py:118)
-    __syncwarp();
-    // codeword words -> rows 2XW.. of the leader column so any lane can read any frame's bits
+    // leaders stage the codeword (and, for the uncoded reference, the payload) words so any lane can read any frame's bits
     if (slot == 0) {
 #pragma unroll
-        for (int w = 0; w < XW; ++w) if (w < xwn) scr[(R2 + w) * 32 + lane] = x[w];
+        for (int w = 0; w < XW; ++w) if (w < xwn) { scr[(R2 + w) * 32 + lane] = x[w]; if (cc.include_uncoded) scr[w * 32 + lane] = pw[w]; }
     }
     __syncwarp();
     unc_err = 0;
@@ -211,13 +228,26 @@ __device__ __forceinline__ void gen_channel(const Code& code, const Tables& tb, 
         __syncwarp();
     }
     const int rounds = (Eeff + N - 1) / N;
+    const int lg_nblk = code.n >= 2 ? code.n - 2 : 0;            // nblk = 2^lg_nblk
     for (int k = 0; k < rounds; ++k) {
         for (int item = lane; item < FPW * nblk; item += 32) {
-            const int f = item / nblk, jb = item - f * nblk;
+            const int f = item >> lg_nblk, jb = item & (nblk - 1);
             const long long fr = fids[f];
             if (fr < 0) continue;
             float z[4];
             normal4(philox4x32_10(make_uint4((uint32_t)fr, (uint32_t)(fr >> 32), (uint32_t)(k * nblk + jb), kPurposeNoise), key), z);
+            if (!nr && N >= 4) {
+                // plain mother code: the four symbols of this block are four neighbouring codeword bits
+                const uint32_t nib = (scr[(R2 + (jb >> 3)) * 32 + f * MP] >> ((jb & 7) * 4)) & 15u;
+                float4 v;
+                v.x = fmaf(cc.sigma, z[0], 1.0f - 2.0f * (float)(nib & 1u)) * cc.scale;
+                v.y = fmaf(cc.sigma, z[1], 1.0f - 2.0f * (float)((nib >> 1) & 1u)) * cc.scale;
+                v.z = fmaf(cc.sigma, z[2], 1.0f - 2.0f * (float)((nib >> 2) & 1u)) * cc.scale;
+                v.w = fmaf(cc.sigma, z[3], 1.0f - 2.0f * (float)((nib >> 3) & 1u)) * cc.scale;
+                if (raw_out) *reinterpret_cast<float4*>(raw_out + (fr - raw_base) * (long long)N + jb * 4) = v;
+                else *reinterpret_cast<float4*>(wm.chan + f * chan_stride(N) + jb * 4) = v;
+                continue;
+            }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int p = jb * 4 + c;          // position inside this round
@@ -335,7 +365,7 @@ struct Sweep {
 
     // write the per-frame results of a finished DL-SCL frame (flip.py:137-141) / count it (run_fer_sweep.py:100-109)
     static __device__ __forceinline__ void finish_dl(const Code& code, const Tables& tb, const SweepArgs& a, const WM& wm, int lane,
-                                                     long long frame, const Best& b, uint32_t n_tried, const uint32_t (&u_sent)[XW], uint32_t (&acc)[cNum]) {
+                                                     long long frame, const Best& b, uint32_t n_tried, const uint32_t (&u_sent)[XW], const AccRef& acc) {
         const long long idx = frame - a.frame_begin;
         if (a.llr == nullptr) {
             bool wrong;
@@ -399,7 +429,7 @@ struct Sweep {
         return slot;
     }
 
-    static __device__ __forceinline__ void flush(const SweepArgs& a, int lane, uint32_t (&acc)[cNum]) {
+    static __device__ __forceinline__ void flush(const SweepArgs& a, int lane, const AccRef& acc) {
         if (a.counters == nullptr) return;
 #pragma unroll
         for (int c = 0; c < cNum; ++c) {
@@ -415,7 +445,7 @@ struct Sweep {
 // TRACE (chosen when DL-SCL retries follow): the list decode records the leaf-LLR trace, and every frame that enters
 // the retry queue gets the |L0| vector of its best path written to abs_store (no SC replay anywhere in DL-SCL).
 template <int MP, int LOGMAX, bool TRACE = false, int HS = DefaultHS<MP>::value>
-__global__ void __launch_bounds__(768) sweep_kernel(const Code code, const Tables tb, const SweepArgs a) {
+__global__ void __launch_bounds__(PB_SWEEP_THREADS) sweep_kernel(const Code code, const Tables tb, const SweepArgs a) {
     using S = Sweep<MP, LOGMAX, HS>;
     using WM = WarpMem<MP, HS>;
     using PathT = typename S::PathT;
@@ -423,10 +453,11 @@ __global__ void __launch_bounds__(768) sweep_kernel(const Code code, const Table
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     WM wm;
-    wm.carve(smem + (size_t)warp * WM::bytes(code.N, 0, TRACE ? code.K : 0),
-             a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WM::gbytes(code.N, code.K), code.N);
+    const size_t kWarpBytes = WM::bytes(code.N, 0, TRACE ? code.K : 0);
+    wm.carve(smem + (size_t)warp * kWarpBytes, a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WM::gbytes(code.N, code.K), code.N);
     const bool leader = (lane & (MP - 1)) == 0;
-    uint32_t acc[cNum];
+    static_assert(cNum * 32 * 4 <= kAccBytes, "counter column");
+    const AccRef acc{reinterpret_cast<uint32_t*>(smem + (size_t)wpc * kWarpBytes + (size_t)warp * kAccBytes) + lane};
 #pragma unroll
     for (int c = 0; c < cNum; ++c) acc[c] = 0;
     const long long ngroups = (a.n_frames + FPW - 1) / FPW;
@@ -505,7 +536,7 @@ __global__ void __launch_bounds__(768) sweep_kernel(const Code code, const Table
 // LLRs are never recomputed by an SC replay.
 // ---------------------------------------------------------------------------------------------------
 template <int MP, int LOGMAX, int HS = 5>
-__global__ void __launch_bounds__(640) dl_retry_kernel(const Code code, const Tables tb, const SweepArgs a) {
+__global__ void __launch_bounds__(PB_RETRY_THREADS) dl_retry_kernel(const Code code, const Tables tb, const SweepArgs a) {
     using S = Sweep<MP, LOGMAX, HS>;
     using WM = WarpMem<MP, HS>;
     using PathT = typename S::PathT;
@@ -514,13 +545,14 @@ __global__ void __launch_bounds__(640) dl_retry_kernel(const Code code, const Ta
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     WM wm;
-    wm.carve(smem + (size_t)warp * WM::bytes(code.N, code.K, code.K),
-             a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WM::gbytes(code.N, code.K), code.N, code.K);
+    const size_t kWarpBytes = WM::bytes(code.N, code.K, code.K);
+    wm.carve(smem + (size_t)warp * kWarpBytes, a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WM::gbytes(code.N, code.K), code.N, code.K);
     const int slot = lane & (MP - 1), fme = lane / MP, gbase = lane & ~(MP - 1);
     float* ab = wm.absl + fme * (code.K + 1);      // |L0| of the reference path of this group's frame
     const bool leader = slot == 0;
     const int K = code.K;
-    uint32_t acc[cNum];
+    static_assert(cNum * 32 * 4 <= kAccBytes, "counter column");
+    const AccRef acc{reinterpret_cast<uint32_t*>(smem + (size_t)wpc * kWarpBytes + (size_t)warp * kAccBytes) + lane};
 #pragma unroll
     for (int c = 0; c < cNum; ++c) acc[c] = 0;
     const unsigned int n_in = min(*a.q_in_count, a.q_capacity);
