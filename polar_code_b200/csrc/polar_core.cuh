@@ -89,11 +89,6 @@ __device__ __forceinline__ float softplus_tail(float L) {
 //            resident warps (~16 KB each) stays L2-resident; moving the two tall heights out of shared memory is
 //            what lifts occupancy from 11 to 32 warps per SM for N = 128.
 // ---------------------------------------------------------------------------
-#ifdef PB_LAUNCH_BOUNDS
-#define PB_LB __launch_bounds__(PB_LAUNCH_BOUNDS)
-#else
-#define PB_LB
-#endif
 // Heights >= HS live in the global scratch.  HS = 5 (heights 5.. global, 30 rows = 3.8 KB of shared memory per warp)
 // lets the register count (64), not shared memory, set the occupancy: 32 warps per SM.  Because the tall levels are
 // evaluated depth-first (Tree::produce) the global rows are written once and read once per use.

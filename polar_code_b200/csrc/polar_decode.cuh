@@ -1,6 +1,8 @@
 // polar_decode.cuh -- the SC / SCL phase loop on top of polar_core.cuh.
 // Reference: dl_scl_polar/polar/scl.py:108-209 (decode_scl), polar/polar.py:130-168 (sc_decode).
 #pragma once
+#include <type_traits>
+
 #include "polar_core.cuh"
 
 namespace pb {
@@ -15,11 +17,22 @@ struct ListDecoder {
     static constexpr int FPW = 32 / MP;
     static constexpr uint32_t GM = (MP >= 32) ? 0xffffffffu : ((1u << MP) - 1u);
 
-    // height-1 pair (a, b) of this lane's path for the EVEN phase `phi` (lazy form of scl.py:64-82)
+    // height-1 pair (a, b) of this lane's path for the EVEN phase `phi` (lazy form of scl.py:64-82).
+    // C1 = true: the caller knows phi = 2 (mod 4), i.e. only height 1 is recomputed (g of the height-2 row).
+    template <bool C1 = false>
     static __device__ __forceinline__ void pair_llr(const Code& code, const WM& wm, PathT& p, int phi, int lane,
                                                     const float* chanf, float& a, float& b) {
         const int n = code.n;
         const int slot = lane & (MP - 1), gbase = lane & ~(MP - 1);
+        if constexpr (C1) {
+            if (n == 2) TreeT::template produce<1, 1, 1>(chanf, p.bw, wm, lane, a, b);      // N = 4: straight from the channel row
+            else {
+                const uint32_t q = (p.P >> 4) & 0xfu;                                         // slot holding height 2
+                TreeT::template produce<1, 1, 32>(wm.ts + 2 * 32 + gbase + q, p.bw, wm, lane, a, b);
+            }
+            p.P = (p.P & ~0xfu) | (uint32_t)slot;
+            return;
+        }
         if (n == 1) { a = chanf[0]; b = chanf[1]; return; }      // N = 2: the channel row is the pair
         const int c = (phi == 0) ? n - 1 : __ffs(phi) - 1;       // first height produced (>= 1)
         if (c == n - 1) {
@@ -54,8 +67,17 @@ struct ListDecoder {
         p.P = (p.P & ~mask) | ((slot * 0x11111111u) & mask);
     }
 
-    // scl.py:84-99 in packed form, for an ODD phase (at least one trailing one)
+    // scl.py:84-99 in packed form, for an ODD phase (at least one trailing one).
+    // T1 = true: the caller knows phi = 1 (mod 4), i.e. exactly one trailing one.
+    template <bool T1 = false>
     static __device__ __forceinline__ void set_bit_odd(const Code& code, PathT& p, int phi, uint32_t bit) {
+        if constexpr (T1) {
+            uint32_t cw[1];
+            ascend<1, BW, 1>(p.bw, bit, cw);
+            if (code.n == 1) p.xh[0] = cw[0];
+            else store_height<1, BW, 1>(p.bw, cw);
+            return;
+        }
         const int t = __ffs(~phi) - 1;  // trailing ones of phi, >= 1
         switch (t) {
 #define PB_CASE(TT)                                                                     \
@@ -109,18 +131,26 @@ struct ListDecoder {
         uint32_t cur_info = 0, cur_fm = 0, cur_fv = 0;   // word phi/32 of the info / force masks
         float a = 0.f, b = 0.f;                          // height-1 pair of the current phase pair
         int jinfo = 0;                                   // index of the current information phase (TRACE)
-        for (int phi = 0; phi < N; ++phi) {
-            if ((phi & 31) == 0) {
-                cur_info = __ldg(imask + (phi >> 5));     // (a dynamic index into the by-value Code would force it into local memory)
-                if constexpr (FORCED) {
+        // One phase.  R >= 0: R = phi mod 4 is a compile-time constant, so the even/odd split, the height-1
+        // recomputation of phases 2 (mod 4) and the one-level partial-sum update of phases 1 (mod 4) need no dispatch
+        // (the plain kernels run the phases in static blocks of four).  R < 0: everything is read from phi -- the
+        // forced / trace-recording kernels keep the compact loop, their code is large enough as it is (measured:
+        // the four-fold body costs them more in instruction fetch than the dispatch it removes).
+        auto phase = [&](const int phi, auto rc) {
+            constexpr int R = decltype(rc)::value;
+            if (R <= 0) {
+                if ((phi & 31) == 0) {
+                    cur_info = __ldg(imask + (phi >> 5));     // (a dynamic index into the by-value Code would force it into local memory)
+                    if constexpr (FORCED) {
 #pragma unroll
-                    for (int k = 0; k < XW; ++k) if (k == (phi >> 5)) { cur_fm = fmask[k]; cur_fv = fval[k]; }
+                        for (int k = 0; k < XW; ++k) if (k == (phi >> 5)) { cur_fm = fmask[k]; cur_fv = fval[k]; }
+                    }
                 }
             }
-            const bool odd = phi & 1;
+            const bool odd = R < 0 ? (phi & 1) : (R & 1);
             // Lanes without a live path run the same code on their own (unused) slot: no divergence, no merges.
             float L;
-            if (!odd) { pair_llr(code, wm, p, phi, lane, chanf, a, b); L = f_op(a, b); }
+            if (!odd) { pair_llr<R == 2>(code, wm, p, phi, lane, chanf, a, b); L = f_op(a, b); }
             else L = g_op(a, b, p.bw[0] & 1u);                   // u_{phi-1} sits in the height-0 field
             const bool is_info = (cur_info >> (phi & 31)) & 1u;
             const bool is_forced = FORCED && is_info && ((cur_fm >> (phi & 31)) & 1u);
@@ -233,8 +263,20 @@ struct ListDecoder {
                 }
             }
             if (!odd) p.bw[0] = (p.bw[0] & ~1u) | bit;           // height-0 left buffer
-            else set_bit_odd(code, p, phi, bit);
+            else set_bit_odd<R == 1>(code, p, phi, bit);
             if constexpr (MP > 1) __syncwarp();
+        };
+        if constexpr (!FORCED && !TRACE) {
+            for (int phi0 = 0; phi0 < N; phi0 += 4) {
+                phase(phi0, std::integral_constant<int, 0>{});
+                phase(phi0 + 1, std::integral_constant<int, 1>{});
+                if (phi0 + 2 < N) {                              // (N = 2 has a single phase pair)
+                    phase(phi0 + 2, std::integral_constant<int, 2>{});
+                    phase(phi0 + 3, std::integral_constant<int, 3>{});
+                }
+            }
+        } else {
+            for (int phi = 0; phi < N; ++phi) phase(phi, std::integral_constant<int, -1>{});
         }
         // final list order = metric order (scl.py:173-174,183-188), ties by the last computed rank
         if constexpr (MP > 1 && METRIC) {

@@ -116,8 +116,10 @@ __device__ __forceinline__ void load_force(const Code& code, const int8_t* force
     }
 }
 
+// N <= 128: compiled for 1024 threads per CTA, i.e. 64 registers -> 32 resident warps per SM (no spills for the plain
+// kernels, a few dozen bytes for the forced ones); N = 256 / 512 keep 16 partial-sum words per path and get 128 registers.
 template <int MP, int LOGMAX, bool FORCED, bool METRIC, int HS = DefaultHS<MP>::value>
-__global__ void PB_LB decode_kernel(const Code code, const Tables tb, const DecodeArgs a) {
+__global__ void __launch_bounds__(LOGMAX <= 7 ? 1024 : 512) decode_kernel(const Code code, const Tables tb, const DecodeArgs a) {
     using Dec = ListDecoder<MP, LOGMAX, FORCED, METRIC, HS>;
     using WM = WarpMem<MP, HS>;
     using PathT = typename Dec::PathT;
