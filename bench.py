@@ -293,14 +293,16 @@ def main() -> None:
     e2e_value = world * Be * Ksteps / (e2e_ms * 1e-3)
     assert torch.equal(h_bits.to(dev), best_bits[:Be]), "host-buffer path and device path disagree"
 
+    NCU_WARP_INSTR_PER_FRAME = 2786    # smsp__inst_executed.sum / frames of decode_kernel<4,7> (profiles/r01_v7_decode_kernel_metrics.txt)
     # ---- roofline -------------------------------------------------------------------------------------
     pk = peaks()
     ms_kernel = ms / Ksteps            # one decode_kernel launch per step, timed with CUDA events on its stream
     ach_gbs = HBM_BYTES_PER_FRAME * B / (ms_kernel * 1e-3) / 1e9
-    # ncu (profiles/r01_v5_decode_kernel_metrics.txt, 1 Mi-frame launch): dram read+write = 594 B per frame,
-    # i.e. the algorithmic bytes (the L2-resident scratch never reaches HBM); scaled here to this launch's B.
+    # ncu (profiles/r01_v7_decode_kernel_metrics.txt, 1 Mi-frame launch): dram read 584 B + write 81 B per frame,
+    # i.e. the algorithmic bytes (the scratch is pinned in L2 by an access-policy window and never reaches HBM);
+    # scaled here to this launch's B.
     roofline = {"bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / pk["hbm_gbs"],
-                "traffic": 594 * B, "traffic_source": "ncu dram__bytes per frame of a 1 Mi-frame launch x B", "peak_source": pk["source"],
+                "traffic": 665 * B, "traffic_source": "ncu dram__bytes per frame of a 1 Mi-frame launch x B", "peak_source": pk["source"],
                 "algorithmic_bytes_per_frame": HBM_BYTES_PER_FRAME,
                 "note": "decode_kernel<4,7> is SM-issue bound, not HBM bound (SURVEY 8(d)): see roofline_issue and profiles/"}
     lane_ops = ELEM_OPS[M] * B / (ms_kernel * 1e-3)
@@ -311,9 +313,11 @@ def main() -> None:
                       "peak": peak_max, "frac": lane_ops / peak_max,
                       "peak_at_measured_clock": props.multi_processor_count * 128 * sm_clock,
                       "frac_at_measured_clock": lane_ops / (props.multi_processor_count * 128 * sm_clock),
-                      "ncu_issue_slots_busy_pct": 77.6, "ncu_warp_instructions_per_frame": 3048,
-                      "note": "SURVEY 8(d) definition (algorithmic element-ops / lane-op peak); the kernel itself keeps 77.6% of the "
-                              "issue slots busy (ncu, profiles/r01_v5_*) -- the gap is per-phase list management, not idle hardware"}
+                      "ncu_issue_slots_busy_pct": 73.3, "ncu_warp_instructions_per_frame": NCU_WARP_INSTR_PER_FRAME,
+                      "issue_slot_frac_live": NCU_WARP_INSTR_PER_FRAME * B / (ms_kernel * 1e-3) / (props.multi_processor_count * 4 * sm_clock),
+                      "note": "SURVEY 8(d) definition (algorithmic element-ops / lane-op peak); the kernel itself keeps 73% of the "
+                              "issue slots busy (ncu, profiles/r01_v7_*; issue_slot_frac_live = ncu warp-instructions per frame x "
+                              "this run's frames/s / (SMs x 4 schedulers x clock)) -- the gap is per-phase list management, not idle hardware"}
 
     extras = {}
     if not args.no_extras and rank == 0 and world == 1:      # informational legs only on the single-GPU run

@@ -173,6 +173,7 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
         const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)e->sms * kb.ctas_per_sm));
         rc = ensure_scratch(e, st, (size_t)std::max(rgrid * kr.wpc, grid * kb.wpc), MP, &p.gscratch);
         if (rc) return rc;
+        pin_scratch_in_l2(e, st, p.gscratch, (size_t)std::max(rgrid * kr.wpc, grid * kb.wpc) * warp_gbytes(MP, code.N, 0), MP >= 2);
         {
             void* args[3] = {(void*)&code, (void*)&e->tb, (void*)&p};
             CUDA_TRY(cudaLaunchKernel(base, dim3(grid), dim3(kb.wpc * 32), args, kb.smem, st));

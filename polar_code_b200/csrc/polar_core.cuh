@@ -131,12 +131,22 @@ struct WarpMem {
         size_t t = (tk && MP > 1) ? (size_t)tk * 32 : 0;
         return tree_bytes(N) + kXchgBytes + x + t;
     }
-    __host__ __device__ static size_t gbytes(int N, int K) {              // global scratch bytes per warp
+    __host__ __device__ static size_t gbytes(int N) {                     // global scratch bytes per warp (tree + channel rows)
         size_t t = (size_t)tree_rows_global(N, HS) * 32 * 4;
         size_t ch = (((size_t)FPW * chan_stride(N) * 4) + 127) & ~(size_t)127;
-        return t + ch + (size_t)K * 32 * 4;
+        return t + ch;
     }
-    __device__ void carve(unsigned char* sbase, unsigned char* gbase, int N, int xk = 0) {
+    __host__ __device__ static size_t hbytes(int K) { return (size_t)K * 32 * 4; }   // trace rows per warp
+    // The scratch buffer of a launch holds the tree/channel areas of all resident warps first (dense, so that the
+    // plain kernels' working set stays L2-resident) and the trace rows of all warps behind them.
+    static __device__ unsigned char* warp_scratch(unsigned char* scratch, int N) {
+        return scratch + ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * gbytes(N);
+    }
+    static __device__ unsigned char* warp_trace(unsigned char* scratch, int N, int K) {
+        const size_t warps = (size_t)gridDim.x * (blockDim.x >> 5);
+        return scratch + warps * gbytes(N) + ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * hbytes(K);
+    }
+    __device__ void carve(unsigned char* sbase, unsigned char* gbase, int N, int xk = 0, unsigned char* hbase = nullptr) {
         ts = reinterpret_cast<float*>(sbase);
         xchg = reinterpret_cast<unsigned long long*>(sbase + tree_bytes(N));
         absl = reinterpret_cast<float*>(sbase + tree_bytes(N) + kXchgBytes);
@@ -144,8 +154,7 @@ struct WarpMem {
         float* g = reinterpret_cast<float*>(gbase);
         tg = g - ((1 << HS) - 2) * 32;
         chan = g + (size_t)tree_rows_global(N, HS) * 32;
-        hist = reinterpret_cast<float*>(gbase + (size_t)tree_rows_global(N, HS) * 32 * 4 +
-                                        ((((size_t)FPW * chan_stride(N) * 4) + 127) & ~(size_t)127));
+        hist = reinterpret_cast<float*>(hbase);
         const int need = 3 * (N >= 32 ? N / 32 : 1);
         scr = (tree_rows_shared(N, HS) >= need) ? ts : g;
     }

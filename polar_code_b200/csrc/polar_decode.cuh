@@ -298,16 +298,40 @@ struct ListDecoder {
     }
 
     // info_llrs of the path that ended in lane `end_lane` (group-uniform), from the trace of a run<true>():
-    // sink(j, L) is called on the group lane with slot == j mod MP.
+    // sink(j, L) is called on the group lane with slot == j mod MP.  Blocks of 32 information phases: first the
+    // lineage chain (shared-memory reads only), then this lane's 32/MP trace loads back to back, then the sinks --
+    // the global loads of a block are all in flight together instead of one L2 round trip per phase.
     template <typename Sink>
     static __device__ __forceinline__ void trace_walk(const Code& code, const WM& wm, int lane, int end_lane, Sink&& sink) {
         const int slot = lane & (MP - 1), gbase = lane & ~(MP - 1);
+        constexpr int PER = 32 / MP;                        // phases of a block this lane is responsible for
         int s = end_lane & (MP - 1);
-        for (int j = code.K - 1; j >= 0; --j) {
-            int w = 0;
-            if constexpr (MP > 1) w = wm.lin[j * 32 + gbase + s];
-            if ((j & (MP - 1)) == slot) sink(j, wm.hist[j * 32 + gbase + w]);
-            s = w;
+        for (int jtop = code.K - 1; jtop >= 0; jtop -= 32) {
+            unsigned long long mine = 0;                    // slots of this lane's phases, 4 bits each, earliest phase lowest
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+                const int j = jtop - t;
+                if (j >= 0) {
+                    int w = 0;
+                    if constexpr (MP > 1) w = wm.lin[j * 32 + gbase + s];
+                    if ((j & (MP - 1)) == slot) mine = (mine << 4) | (unsigned long long)w;
+                    s = w;
+                }
+            }
+            // this lane's phases of the block, ascending: j0, j0 + MP, ...
+            const int jlo = jtop - 31 > 0 ? jtop - 31 : 0;
+            const int j0 = jlo + ((slot - jlo) & (MP - 1));
+            float v[PER];
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int j = j0 + i * MP;
+                v[i] = (j <= jtop) ? wm.hist[j * 32 + gbase + (int)((mine >> (4 * i)) & 15ull)] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int j = j0 + i * MP;
+                if (j <= jtop) sink(j, v[i]);
+            }
         }
     }
 

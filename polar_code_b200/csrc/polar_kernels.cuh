@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(LOGMAX <= 7 ? 1024 : 512) decode_kernel(const 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpc = blockDim.x >> 5;
     WM wm;
-    wm.carve(smem + (size_t)warp * WM::bytes(code.N), a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WM::gbytes(code.N, code.K), code.N);
+    wm.carve(smem + (size_t)warp * WM::bytes(code.N), WM::warp_scratch(a.gscratch, code.N), code.N);
     const int K = code.K, M = code.M;
     const int xwn = code.N >= 32 ? code.N / 32 : 1;
     const int64_t ngroups = (a.B + FPW - 1) / FPW;

@@ -454,7 +454,8 @@ __global__ void __launch_bounds__(PB_SWEEP_THREADS) sweep_kernel(const Code code
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     WM wm;
     const size_t kWarpBytes = WM::bytes(code.N, 0, TRACE ? code.K : 0);
-    wm.carve(smem + (size_t)warp * kWarpBytes, a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WM::gbytes(code.N, code.K), code.N);
+    wm.carve(smem + (size_t)warp * kWarpBytes, WM::warp_scratch(a.gscratch, code.N), code.N, 0,
+             TRACE ? WM::warp_trace(a.gscratch, code.N, code.K) : nullptr);
     const bool leader = (lane & (MP - 1)) == 0;
     static_assert(cNum * 32 * 4 <= kAccBytes, "counter column");
     const AccRef acc{reinterpret_cast<uint32_t*>(smem + (size_t)wpc * kWarpBytes + (size_t)warp * kAccBytes) + lane};
@@ -546,7 +547,7 @@ __global__ void __launch_bounds__(PB_RETRY_THREADS) dl_retry_kernel(const Code c
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     WM wm;
     const size_t kWarpBytes = WM::bytes(code.N, code.K, code.K);
-    wm.carve(smem + (size_t)warp * kWarpBytes, a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WM::gbytes(code.N, code.K), code.N, code.K);
+    wm.carve(smem + (size_t)warp * kWarpBytes, WM::warp_scratch(a.gscratch, code.N), code.N, code.K, WM::warp_trace(a.gscratch, code.N, code.K));
     const int slot = lane & (MP - 1), fme = lane / MP, gbase = lane & ~(MP - 1);
     float* ab = wm.absl + fme * (code.K + 1);      // |L0| of the reference path of this group's frame
     const bool leader = slot == 0;
@@ -694,7 +695,7 @@ __global__ void channel_kernel(const Code code, const Tables tb, const SweepArgs
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     using WM = WarpMem<MP, 5>;
     WM wm;
-    wm.carve(smem + (size_t)warp * WM::bytes(code.N), a.gscratch + ((size_t)blockIdx.x * wpc + warp) * WM::gbytes(code.N, code.K), code.N);
+    wm.carve(smem + (size_t)warp * WM::bytes(code.N), WM::warp_scratch(a.gscratch, code.N), code.N);
     const long long ngroups = (a.n_frames + FPW - 1) / FPW;
     for (long long g = (long long)blockIdx.x * wpc + warp; g < ngroups; g += (long long)gridDim.x * wpc) {
         const long long idx = g * FPW + lane / MP;
