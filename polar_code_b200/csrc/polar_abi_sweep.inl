@@ -120,11 +120,11 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
     const void* base = big ? pb_sweep_kernel_9(MP, trace ? 2 : 0) : pb_sweep_kernel_7(MP, trace ? 2 : 0);
     const void* round = big ? pb_sweep_kernel_9(MP, 1) : pb_sweep_kernel_7(MP, 1);
     KernelCfg kb, kr{};
-    int rc = choose_cfg(e, base, MP, trace ? 6 : 4, warp_bytes(MP, code.N, 0, false, trace ? code.K : 0) + kAccBytes, &kb);
+    int rc = choose_cfg(e, base, MP, trace ? 6 : 4, warp_bytes(MP, code.N, 0, false, trace ? code.K : 0) + acc_bytes(MP), &kb);
     if (rc) return rc;
     int rgrid = 0;
     if (a.retries > 0) {
-        rc = choose_cfg(e, round, MP, 5, warp_bytes(MP, code.N, code.K, true, code.K) + kAccBytes, &kr);
+        rc = choose_cfg(e, round, MP, 5, warp_bytes(MP, code.N, code.K, true, code.K) + acc_bytes(MP), &kr);
         if (rc) return rc;
         rgrid = std::max(1, e->sms * kr.ctas_per_sm);
     }

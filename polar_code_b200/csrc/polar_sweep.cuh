@@ -95,13 +95,15 @@ struct SweepArgs {
 template <int XW> struct DlEntry { DlEntryHdr h; uint32_t u[XW]; uint32_t tried[XW]; uint32_t u_sent[XW]; uint32_t store; uint32_t pad; };
 
 // counters indices (include/polar_b200.h)
-// Per-lane counter column in shared memory (c-th counter of this lane at p[c*32]): keeps the 12 running totals out of
-// the register file of the persistent kernels; flush() reduces them over the warp and adds them to the global block.
+// Counter column of a frame group in shared memory (c-th counter of group g of the warp at base[c*FPW + g]; only the
+// group leader touches it): keeps the 12 running totals out of the register file of the persistent kernels; flush()
+// reduces the leaders' columns over the warp and adds them to the global block.
 struct AccRef {
     uint32_t* p;
-    __device__ __forceinline__ uint32_t& operator[](int c) const { return p[c * 32]; }
+    int stride;
+    __device__ __forceinline__ uint32_t& operator[](int c) const { return p[c * stride]; }
 };
-constexpr int kAccBytes = 12 * 32 * 4;
+__host__ __device__ constexpr int acc_bytes(int MP) { return 12 * (32 / MP) * 4; }
 
 enum { cFrames = 0, cSclFe, cSclBe, cDlFe, cDlBe, cUncFe, cUncBe, cDlWork, cNearTie, cSclUndet, cDlUndet, cRankTie, cNum };
 
@@ -111,7 +113,7 @@ enum { cFrames = 0, cSclFe, cSclBe, cDlFe, cDlBe, cUncFe, cUncBe, cDlWork, cNear
 // bit-error count.  Scratch: the (not yet used) tree area.
 // ---------------------------------------------------------------------------------------------------
 #ifndef PB_RETRY_THREADS
-#define PB_RETRY_THREADS 640
+#define PB_RETRY_THREADS 768
 #endif
 #ifndef PB_SWEEP_THREADS
 #define PB_SWEEP_THREADS 1024
@@ -433,7 +435,7 @@ struct Sweep {
         if (a.counters == nullptr) return;
 #pragma unroll
         for (int c = 0; c < cNum; ++c) {
-            const uint32_t s = __reduce_add_sync(kFull, acc[c]);
+            const uint32_t s = __reduce_add_sync(kFull, (lane & (MP - 1)) == 0 ? acc[c] : 0u);
             if (lane == 0 && s) atomicAdd(&a.counters[c], (unsigned long long)s);
         }
     }
@@ -457,10 +459,13 @@ __global__ void __launch_bounds__(PB_SWEEP_THREADS) sweep_kernel(const Code code
     wm.carve(smem + (size_t)warp * kWarpBytes, WM::warp_scratch(a.gscratch, code.N), code.N, 0,
              TRACE ? WM::warp_trace(a.gscratch, code.N, code.K) : nullptr);
     const bool leader = (lane & (MP - 1)) == 0;
-    static_assert(cNum * 32 * 4 <= kAccBytes, "counter column");
-    const AccRef acc{reinterpret_cast<uint32_t*>(smem + (size_t)wpc * kWarpBytes + (size_t)warp * kAccBytes) + lane};
+    static_assert(cNum <= 12, "counter column");
+    const AccRef acc{reinterpret_cast<uint32_t*>(smem + (size_t)wpc * kWarpBytes + (size_t)warp * acc_bytes(MP)) + lane / MP, FPW};
+    if ((lane & (MP - 1)) == 0) {
 #pragma unroll
-    for (int c = 0; c < cNum; ++c) acc[c] = 0;
+        for (int c = 0; c < cNum; ++c) acc[c] = 0;
+    }
+    __syncwarp();
     const long long ngroups = (a.n_frames + FPW - 1) / FPW;
     for (long long g = (long long)blockIdx.x * wpc + warp; g < ngroups; g += (long long)gridDim.x * wpc) {
         const long long idx = g * FPW + lane / MP;
@@ -552,10 +557,13 @@ __global__ void __launch_bounds__(PB_RETRY_THREADS) dl_retry_kernel(const Code c
     float* ab = wm.absl + fme * (code.K + 1);      // |L0| of the reference path of this group's frame
     const bool leader = slot == 0;
     const int K = code.K;
-    static_assert(cNum * 32 * 4 <= kAccBytes, "counter column");
-    const AccRef acc{reinterpret_cast<uint32_t*>(smem + (size_t)wpc * kWarpBytes + (size_t)warp * kAccBytes) + lane};
+    static_assert(cNum <= 12, "counter column");
+    const AccRef acc{reinterpret_cast<uint32_t*>(smem + (size_t)wpc * kWarpBytes + (size_t)warp * acc_bytes(MP)) + lane / MP, FPW};
+    if ((lane & (MP - 1)) == 0) {
 #pragma unroll
-    for (int c = 0; c < cNum; ++c) acc[c] = 0;
+        for (int c = 0; c < cNum; ++c) acc[c] = 0;
+    }
+    __syncwarp();
     const unsigned int n_in = min(*a.q_in_count, a.q_capacity);
 
     // state of the frame this group is working on (identical on all lanes of the group)
