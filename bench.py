@@ -21,6 +21,11 @@ import threading
 import time
 from pathlib import Path
 
+# rank 0 prints exactly ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner
+# with plain stdio), so the real stdout is kept on a private descriptor and fd 1 is pointed at stderr for everything else.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent
@@ -147,7 +152,7 @@ def run_reference(args) -> None:
         "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
 def workload_config(frames_per_step: int, gpus: int, cpu: bool = False) -> dict:
@@ -341,7 +346,7 @@ def main() -> None:
             line["cpu_baseline"] = cb
         if extras:
             line["extras"] = extras
-        print(json.dumps(line))
+        print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
