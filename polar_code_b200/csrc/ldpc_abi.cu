@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/polar_b200.h"
@@ -42,6 +43,11 @@ struct pb200_ldpc {
     int* d_row_ptr = nullptr;
     int* d_col_idx = nullptr;
     std::map<int, GenDev> gens;        // per payload length k
+    // layers of consecutive, mutually column-disjoint rows (group-per-frame kernels); G = 0: thread-per-frame only
+    int nl = 0, G = 0, lgG = 0;
+    bool weight4 = false;              // every row has exactly four ones (static-weight kernels)
+    int* d_layer_ptr = nullptr;
+    std::map<std::tuple<int, unsigned long long>, unsigned long long*> crc_tabs;   // (kp, poly) -> nibble table
     std::map<cudaStream_t, std::pair<unsigned char*, size_t>> scratch;   // global state for codes too large for smem
 };
 
@@ -97,6 +103,38 @@ extern "C" int pb200_ldpc_create(pb200_ldpc** out, int device, const uint8_t* h_
         pb200_ldpc_destroy(e);
         return lfail(PB200_ECUDA, "table upload failed: %s", cudaGetErrorString(ce));
     }
+    // greedy layering: a row joins the current layer while it shares no column with it (and the layer has < 32 rows)
+    {
+        std::vector<int> lp{0};
+        std::vector<char> used(n, 0);
+        int width = 0, maxw = 0;
+        for (int r = 0; r < m; ++r) {
+            bool clash = width >= 32;
+            for (int q = rp[r]; q < rp[r + 1] && !clash; ++q) clash = used[ci[q]] != 0;
+            if (clash) {
+                lp.push_back(r);
+                std::fill(used.begin(), used.end(), 0);
+                width = 0;
+            }
+            for (int q = rp[r]; q < rp[r + 1]; ++q) used[ci[q]] = 1;
+            ++width;
+            maxw = std::max(maxw, width);
+        }
+        lp.push_back(m);
+        e->nl = (int)lp.size() - 1;
+        e->weight4 = true;
+        for (int r = 0; r < m; ++r) e->weight4 = e->weight4 && (rp[r + 1] - rp[r] == 4);
+        if (maxw >= 4 && e->nnz > 0) {        // narrow layers (Z < 4, unstructured H): one thread per frame is the better mapping
+            int G = 4, lg = 2;
+            while (G < maxw) { G <<= 1; ++lg; }
+            e->G = G; e->lgG = lg;
+            if ((ce = cudaMalloc((void**)&e->d_layer_ptr, lp.size() * 4)) != cudaSuccess ||
+                (ce = cudaMemcpy(e->d_layer_ptr, lp.data(), lp.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+                pb200_ldpc_destroy(e);
+                return lfail(PB200_ECUDA, "layer table upload failed: %s", cudaGetErrorString(ce));
+            }
+        }
+    }
     *out = e;
     return PB200_OK;
 }
@@ -104,7 +142,8 @@ extern "C" int pb200_ldpc_create(pb200_ldpc** out, int device, const uint8_t* h_
 extern "C" void pb200_ldpc_destroy(pb200_ldpc* e) {
     if (!e) return;
     cudaSetDevice(e->device);
-    cudaFree(e->d_row_ptr); cudaFree(e->d_col_idx);
+    cudaFree(e->d_row_ptr); cudaFree(e->d_col_idx); cudaFree(e->d_layer_ptr);
+    for (auto& kv : e->crc_tabs) cudaFree(kv.second);
     for (auto& kv : e->gens) { cudaFree(kv.second.d_G); cudaFree(kv.second.d_C); }
     for (auto& kv : e->scratch) cudaFree(kv.second.first);
     delete e;
@@ -254,6 +293,34 @@ static int ensure_scratch(pb200_ldpc* e, cudaStream_t st, size_t need, unsigned 
     return PB200_OK;
 }
 
+// Launch shape of the group-per-frame kernels: warps per CTA such that the frame states fit in shared memory.
+// ok = false: the state of even one warp does not fit -> use the thread-per-frame kernels.
+static int plan_group_launch(pb200_ldpc* e, const void* fn, size_t frame_bytes, int64_t frames, LdpcLaunch* L, bool* ok) {
+    *ok = false;
+    if (e->G == 0) return PB200_OK;
+    const int fpw = 32 / e->G;
+    const size_t cap = 200 * 1024, per_warp = frame_bytes * fpw;
+    int wpc = (int)std::min<size_t>(8, cap / per_warp);
+    if (wpc < 1) return PB200_OK;
+    L->threads = wpc * 32;
+    L->smem = per_warp * wpc;
+    L->global = false;
+    LCUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+    int per_sm = 0;
+    LCUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, L->threads, L->smem));
+    if (per_sm < 1) return PB200_OK;
+    const int64_t batches = (frames + fpw - 1) / fpw;
+    L->blocks = (int)grid_for(batches, wpc, e->sms * per_sm);
+    *ok = true;
+    return PB200_OK;
+}
+
+static LdpcLayers layers_of(const pb200_ldpc* e) {
+    LdpcLayers L;
+    L.nl = e->nl; L.G = e->G; L.lgG = e->lgG; L.layer_ptr = e->d_layer_ptr;
+    return L;
+}
+
 extern "C" int pb200_ldpc_decode_batch(pb200_ldpc* e, const double* d_llr, int64_t B, int in_len, int max_iter, double alpha,
                                        int early_stop, uint8_t* d_hard, double* d_posterior, int32_t* d_iters, uint8_t* d_ok,
                                        void* stream) {
@@ -263,11 +330,21 @@ extern "C" int pb200_ldpc_decode_batch(pb200_ldpc* e, const double* d_llr, int64
     if (!d_llr && in_len > 0) return lfail(PB200_EINVAL, "llr is NULL");
     LCUDA_TRY(cudaSetDevice(e->device));
     LdpcLaunch L;
-    int rc = plan_launch(e, (const void*)ldpc_decode_kernel, (size_t)(e->n + e->m) * 8, B, &L);
-    if (rc) return rc;
     LdpcDecodeArgs a{};
     a.llr = d_llr; a.B = B; a.in_len = in_len; a.max_iter = max_iter; a.early_stop = early_stop; a.alpha = alpha;
     a.hard = d_hard; a.posterior = d_posterior; a.iters = d_iters; a.ok = d_ok;
+    bool grouped = false;
+    const void* gfn = e->weight4 ? (const void*)ldpc_decode_group_kernel<4> : (const void*)ldpc_decode_group_kernel<0>;
+    int rc = plan_group_launch(e, gfn, ldpc_group_frame_bytes(e->n, e->m, 0, 0, 0), B, &L, &grouped);
+    if (rc) return rc;
+    if (grouped) {
+        if (e->weight4) ldpc_decode_group_kernel<4><<<L.blocks, L.threads, L.smem, (cudaStream_t)stream>>>(code_of(e, e->n - e->m), layers_of(e), a);
+        else ldpc_decode_group_kernel<0><<<L.blocks, L.threads, L.smem, (cudaStream_t)stream>>>(code_of(e, e->n - e->m), layers_of(e), a);
+        LCUDA_TRY(cudaGetLastError());
+        return PB200_OK;
+    }
+    rc = plan_launch(e, (const void*)ldpc_decode_kernel, (size_t)(e->n + e->m) * 8, B, &L);
+    if (rc) return rc;
     if (L.global) {
         unsigned char* p;
         rc = ensure_scratch(e, (cudaStream_t)stream, (size_t)(e->n + e->m) * 8 * L.threads * L.blocks, &p);
@@ -276,6 +353,38 @@ extern "C" int pb200_ldpc_decode_batch(pb200_ldpc* e, const double* d_llr, int64
     }
     ldpc_decode_kernel<<<L.blocks, L.threads, L.smem, (cudaStream_t)stream>>>(code_of(e, e->n - e->m), a);
     LCUDA_TRY(cudaGetLastError());
+    return PB200_OK;
+}
+
+// CRC nibble table for the grouped sweep: row (q, v) = remainder contribution of payload nibble q holding value v
+// (crc.py:19-37 is linear with a zero initial register): bit j of the payload contributes x^(kp-1-j+deg) mod g.
+static int get_crc_tab(pb200_ldpc* e, int kp, unsigned long long poly, int deg, LdpcCrcTab* out) {
+    auto key = std::make_tuple(kp, poly);
+    auto it = e->crc_tabs.find(key);
+    const int nq = (kp + 3) / 4;
+    if (it == e->crc_tabs.end()) {
+        const unsigned long long mask = deg >= 64 ? ~0ull : ((1ull << deg) - 1ull), low = poly & mask;
+        std::vector<unsigned long long> bitrem(kp);
+        // x^deg mod g, then multiply by x step by step: bit kp-1 first (exponent deg), bit 0 last
+        unsigned long long r = low;                       // x^deg mod g
+        for (int j = kp - 1; j >= 0; --j) {
+            bitrem[j] = r;
+            const unsigned long long top = (r >> (deg - 1)) & 1ull;
+            r = (r << 1) & mask;
+            if (top) r ^= low;
+        }
+        std::vector<unsigned long long> tab((size_t)nq * 16, 0);
+        for (int q = 0; q < nq; ++q)
+            for (int v = 0; v < 16; ++v)
+                for (int b = 0; b < 4; ++b)
+                    if (((v >> b) & 1) && q * 4 + b < kp) tab[(size_t)q * 16 + v] ^= bitrem[q * 4 + b];
+        unsigned long long* d = nullptr;
+        LCUDA_TRY(cudaMalloc((void**)&d, tab.size() * 8));
+        LCUDA_TRY(cudaMemcpy(d, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice));
+        it = e->crc_tabs.emplace(key, d).first;
+    }
+    out->tab = it->second;
+    out->nq = nq;
     return PB200_OK;
 }
 
@@ -312,8 +421,19 @@ static int sweep_common(pb200_ldpc* e, const pb200_ldpc_sweep_cfg* c, int64_t* d
     const int nw = (e->n + 31) / 32;
     LdpcLaunch L;
     const size_t bpt = (size_t)(e->n + e->m) * 8 + (size_t)(gd->g.kw + nw) * 4;
-    rc = plan_launch(e, (const void*)ldpc_sweep_kernel, bpt, c->n_frames, &L);
+    bool grouped = false;
+    const void* gfn = e->weight4 ? (const void*)ldpc_sweep_group_kernel<4> : (const void*)ldpc_sweep_group_kernel<0>;
+    rc = plan_group_launch(e, gfn, ldpc_group_frame_bytes(e->n, e->m, c->E, gd->g.kw, nw), c->n_frames, &L, &grouped);
     if (rc) return rc;
+    LdpcCrcTab ct{nullptr, 0};
+    if (grouped && deg > 0) {
+        rc = get_crc_tab(e, c->k_payload, poly, deg, &ct);
+        if (rc) return rc;
+    }
+    if (!grouped) {
+        rc = plan_launch(e, (const void*)ldpc_sweep_kernel, bpt, c->n_frames, &L);
+        if (rc) return rc;
+    }
     LdpcSweepArgs a{};
     a.frame_begin = c->frame_begin; a.n_frames = c->n_frames;
     a.k0 = (uint32_t)(c->seed & 0xffffffffu);
@@ -326,6 +446,12 @@ static int sweep_common(pb200_ldpc* e, const pb200_ldpc_sweep_cfg* c, int64_t* d
     a.frame_bit_errors = d_fbe; a.frame_work = d_fwork;
     a.payload_out = chan_only ? d_payload : nullptr;
     a.llr_out = chan_only ? d_llr : nullptr;
+    if (grouped) {
+        if (e->weight4) ldpc_sweep_group_kernel<4><<<L.blocks, L.threads, L.smem, (cudaStream_t)stream>>>(code_of(e, k), gd->g, layers_of(e), ct, a);
+        else ldpc_sweep_group_kernel<0><<<L.blocks, L.threads, L.smem, (cudaStream_t)stream>>>(code_of(e, k), gd->g, layers_of(e), ct, a);
+        LCUDA_TRY(cudaGetLastError());
+        return PB200_OK;
+    }
     if (L.global) {
         unsigned char* p;
         const size_t tot = (size_t)L.threads * L.blocks;

@@ -12,6 +12,8 @@ binomial confidence interval), not draw for draw.
 from __future__ import annotations
 
 import argparse
+import sys
+import time
 from pathlib import Path
 from typing import Dict, List, Optional, Tuple
 
@@ -56,9 +58,14 @@ def sweep_rows(args: argparse.Namespace) -> List[Dict[str, float]]:
     rank, _ = mc.world()
     rows: List[Dict[str, float]] = []
     for snr_db in _snr_grid(args):
+        t0 = time.perf_counter()
         c = mc.fer_point(eng, M=args.M, snr_db=float(snr_db), frames=args.frames, seed=args.seed, retries=args.retries,
                          beta=beta, include_uncoded=args.include_uncoded, k_payload=payload_bits)
+        dt = time.perf_counter() - t0            # includes the counter all-reduce and the device->host read
         frames = int(c[0])
+        if rank == 0:                             # timing goes to stderr: stdout keeps the reference's lines only
+            print(f"[b200] {snr_db:.2f} dB: {frames} frames in {dt:.3f} s = {frames / max(dt, 1e-9):.3e} frames/s "
+                  f"over {mc.world()[1]} GPU(s)", file=sys.stderr)
         bits_coded = frames * cfg.K
         nan = float("nan")
         row = {"snr_db": snr_db,
