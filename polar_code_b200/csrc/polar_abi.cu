@@ -368,7 +368,9 @@ static void pin_scratch_in_l2(pb200_engine* e, cudaStream_t st, unsigned char* s
     }
     if (e->l2_window_max <= 0 || e->l2_persist_max <= 0) return;
     if (!e->l2_limit_set) {
-        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min((size_t)e->l2_persist_max, bytes)) != cudaSuccess) cudaGetLastError();
+        // the whole set-aside the device allows: later launches of this engine may bring a larger scratch, and the
+        // window's hitRatio below is computed against this size
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)e->l2_persist_max) != cudaSuccess) cudaGetLastError();
         e->l2_limit_set = true;
     }
     auto& cur = e->l2_window[st];

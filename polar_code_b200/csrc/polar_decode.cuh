@@ -131,14 +131,15 @@ struct ListDecoder {
         uint32_t cur_info = 0, cur_fm = 0, cur_fv = 0;   // word phi/32 of the info / force masks
         float a = 0.f, b = 0.f;                          // height-1 pair of the current phase pair
         int jinfo = 0;                                   // index of the current information phase (TRACE)
-        // One phase.  R >= 0: R = phi mod 4 is a compile-time constant, so the even/odd split, the height-1
-        // recomputation of phases 2 (mod 4) and the one-level partial-sum update of phases 1 (mod 4) need no dispatch
-        // (the plain kernels run the phases in static blocks of four).  R < 0: everything is read from phi -- the
+        // One phase.  R = 0..3: R = phi mod 4 is a compile-time constant, so the even/odd split, the height-1
+        // recomputation of phases 2 (mod 4) and the one-level partial-sum update of phases 1 (mod 4) need no dispatch.
+        // R = 10 / 11: even / odd phase of a pair whose kind (`half`) is a run-time, warp-uniform flag.
+        // R < 0: everything is read from phi -- the
         // forced / trace-recording kernels keep the compact loop, their code is large enough as it is (measured:
         // the four-fold body costs them more in instruction fetch than the dispatch it removes).
-        auto phase = [&](const int phi, auto rc) {
+        auto phase = [&](const int phi, auto rc, const int half) {
             constexpr int R = decltype(rc)::value;
-            if (R <= 0) {
+            if (R <= 0 || R == 10) {
                 if ((phi & 31) == 0) {
                     cur_info = __ldg(imask + (phi >> 5));     // (a dynamic index into the by-value Code would force it into local memory)
                     if constexpr (FORCED) {
@@ -150,7 +151,13 @@ struct ListDecoder {
             const bool odd = R < 0 ? (phi & 1) : (R & 1);
             // Lanes without a live path run the same code on their own (unused) slot: no divergence, no merges.
             float L;
-            if (!odd) { pair_llr<R == 2>(code, wm, p, phi, lane, chanf, a, b); L = f_op(a, b); }
+            if (!odd) {
+                if constexpr (R == 10) {                         // even phase of a pair: half = 1 <=> phi = 2 (mod 4)
+                    if (half) pair_llr<true>(code, wm, p, phi, lane, chanf, a, b);
+                    else pair_llr<false>(code, wm, p, phi, lane, chanf, a, b);
+                } else pair_llr<R == 2>(code, wm, p, phi, lane, chanf, a, b);
+                L = f_op(a, b);
+            }
             else L = g_op(a, b, p.bw[0] & 1u);                   // u_{phi-1} sits in the height-0 field
             const bool is_info = (cur_info >> (phi & 31)) & 1u;
             const bool is_forced = FORCED && is_info && ((cur_fm >> (phi & 31)) & 1u);
@@ -263,20 +270,36 @@ struct ListDecoder {
                 }
             }
             if (!odd) p.bw[0] = (p.bw[0] & ~1u) | bit;           // height-0 left buffer
-            else set_bit_odd<R == 1>(code, p, phi, bit);
+            else if constexpr (R == 11) {                        // odd phase of a pair: half = 0 <=> phi = 1 (mod 4)
+                if (half) set_bit_odd<false>(code, p, phi, bit);
+                else set_bit_odd<true>(code, p, phi, bit);
+            } else set_bit_odd<R == 1>(code, p, phi, bit);
             if constexpr (MP > 1) __syncwarp();
         };
-        if constexpr (!FORCED && !TRACE) {
+        if constexpr (!FORCED && !TRACE && MP == 1) {
+            // thread-per-frame kernels (no rank/clone code): fully static blocks of four phases (measured +7 % over pairs)
             for (int phi0 = 0; phi0 < N; phi0 += 4) {
-                phase(phi0, std::integral_constant<int, 0>{});
-                phase(phi0 + 1, std::integral_constant<int, 1>{});
+                phase(phi0, std::integral_constant<int, 0>{}, 0);
+                phase(phi0 + 1, std::integral_constant<int, 1>{}, 0);
                 if (phi0 + 2 < N) {                              // (N = 2 has a single phase pair)
-                    phase(phi0 + 2, std::integral_constant<int, 2>{});
-                    phase(phi0 + 3, std::integral_constant<int, 3>{});
+                    phase(phi0 + 2, std::integral_constant<int, 2>{}, 1);
+                    phase(phi0 + 3, std::integral_constant<int, 3>{}, 1);
                 }
             }
+        } else if constexpr (!FORCED && !TRACE) {
+            // list kernels: phase pairs.  Even/odd is static; which of the two pair kinds it is (phi = 0/1 or 2/3 mod 4)
+            // is one uniform branch around the statically specialised recompute / partial-sum update -- two copies of
+            // the rank/clone code instead of four.  Measured on M = 4: 2 915 instead of 2 786 warp-instructions per
+            // frame, but no_instruction stalls 0.31 instead of 1.16 per issue and 78 % instead of 73 % issue slots busy
+            // (+3.6 % frames/s).
+#pragma unroll 1
+            for (int phi0 = 0; phi0 < N; phi0 += 2) {
+                const int half = (phi0 >> 1) & 1;
+                phase(phi0, std::integral_constant<int, 10>{}, half);
+                phase(phi0 + 1, std::integral_constant<int, 11>{}, half);
+            }
         } else {
-            for (int phi = 0; phi < N; ++phi) phase(phi, std::integral_constant<int, -1>{});
+            for (int phi = 0; phi < N; ++phi) phase(phi, std::integral_constant<int, -1>{}, 0);
         }
         // final list order = metric order (scl.py:173-174,183-188), ties by the last computed rank
         if constexpr (MP > 1 && METRIC) {
