@@ -550,7 +550,9 @@ extern "C" int pb200_scl_decode_host(pb200_engine* e, const float* h_llr, int64_
     if (B == 0) return PB200_OK;
     CUDA_TRY(cudaSetDevice(e->device));
     const int K = e->code.K;
-    const int64_t chunk = std::min<int64_t>(B, 1 << 18);
+    // 2^16 frames (32 MiB of LLRs) per chunk: the pipeline's fill (first copy-in) and drain (last decode + copy-out)
+    // are not overlapped, so small chunks keep them short; a chunk still fills the GPU (8 192 warps of work)
+    const int64_t chunk = std::min<int64_t>(B, 1 << 16);
     if (e->stage_frames < chunk || e->stage_len != in_len) {
         for (int i = 0; i < 3; ++i) {
             cudaFree(e->d_stage_llr[i]); cudaFree(e->d_stage_bits[i]); cudaFree(e->d_stage_ok[i]); cudaFree(e->d_stage_flags[i]);
