@@ -188,6 +188,8 @@ def main() -> None:
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the polar_b200 engine has no CPU fallback")
     torch.cuda.set_device(local)
+    from polar_code_b200.montecarlo import bind_to_gpu_numa
+    numa_cpus = bind_to_gpu_numa(local) if world > 1 else None     # host buffers of a rank live on its GPU's socket
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -336,6 +338,7 @@ def main() -> None:
             "ms_per_step": ms / Ksteps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(B, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": Be * N * 4, "d2h_bytes_per_step": Be * (K + 1 + 4),
+                    "rank0_cpu_affinity": numa_cpus,
                     "frames_per_step_per_gpu": Be, "ms_per_step": e2e_ms / Ksteps,
                     "call": "pb200_scl_decode_host (pinned host LLRs -> best_bits, crc_ok, flags on the host)"},
             "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "roofline_issue": roofline_issue,

@@ -30,6 +30,31 @@ def world() -> Tuple[int, int]:
     return 0, 1
 
 
+def bind_to_gpu_numa(device_index: int) -> Optional[str]:
+    """Pin this process to the CPUs next to its GPU (sysfs `local_cpulist` of the GPU's PCI function), so that the
+    pinned host buffers it allocates afterwards are first-touched on that NUMA node and every rank's host<->device
+    copies stay on its own socket.  Returns the cpulist applied, or None when sysfs has nothing to say
+    (single-socket box, container without the PCI tree)."""
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        text = open(path).read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return text
+    except Exception:
+        return None
+
+
 def maybe_init_distributed() -> Tuple[int, int]:
     """Join the torchrun rendezvous if this process was launched by it (one process per GPU, NCCL)."""
     ws = int(os.environ.get("WORLD_SIZE", "1"))
@@ -37,6 +62,7 @@ def maybe_init_distributed() -> Tuple[int, int]:
         local = int(os.environ.get("LOCAL_RANK", "0"))
         if torch.cuda.is_available():
             torch.cuda.set_device(local)
+            bind_to_gpu_numa(local)
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         else:
             dist.init_process_group("gloo")
