@@ -121,14 +121,22 @@ struct WarpMem {
     float* scr;           // >= 3*max(N/32,1) lane-interleaved rows of scratch for the encoder / bit stash
     unsigned long long* xchg;  // [32][2] candidate keys for the rank exchange / small per-frame scratch (shared)
     float* absl;          // [FPW][xk+1] DL-SCL only: |L0| of the reference path (flip.py:102) (shared)
-    uint8_t* lin;         // [tk][32] trace mode only: slot a surviving path came from at info phase j (shared)
+    uint32_t* lin;        // [tk][4] trace mode only: ballot words (bit planes 0..2) of the slot each surviving path came
+                          // from at info phase j (shared; written by lane 0)
     float* hist;          // [K][32] trace mode only: leaf LLR every slot saw at info phase j (global scratch)
     static constexpr int FPW = 32 / MP;
     __host__ __device__ static size_t tree_bytes(int N) { return (size_t)tree_rows_shared(N, HS) * 32 * 4; }
-    // shared bytes per warp: xk > 0 adds the |L0| rows, tk > 0 the lineage bytes of the trace (info_llrs without a replay)
+    // The |L0| rows of the DL-SCL retry kernel are only live BETWEEN two list decodes (trace walk -> beta scoring), when
+    // the tree rows are dead: they alias the shared tree area behind the stash rows whenever they fit there.
+    __host__ __device__ static size_t absl_bytes(int xk) { return xk ? (((size_t)FPW * (xk + 1) * 4 + 15) & ~(size_t)15) : 0; }
+    __host__ __device__ static size_t stash_bytes(int N) { return (size_t)3 * (N >= 32 ? N / 32 : 1) * 32 * 4; }
+    __host__ __device__ static bool absl_aliases_tree(int N, int xk) {
+        return xk && tree_rows_shared(N, HS) * 32 * 4 >= (int)(stash_bytes(N) + absl_bytes(xk));
+    }
+    // shared bytes per warp: xk > 0 adds the |L0| rows, tk > 0 the lineage words of the trace (info_llrs without a replay)
     __host__ __device__ static size_t bytes(int N, int xk = 0, int tk = 0) {
-        size_t x = xk ? (((size_t)FPW * (xk + 1) * 4 + 15) & ~(size_t)15) : 0;
-        size_t t = (tk && MP > 1) ? (size_t)tk * 32 : 0;
+        size_t x = absl_aliases_tree(N, xk) ? 0 : absl_bytes(xk);
+        size_t t = (tk && MP > 1) ? (size_t)tk * 16 : 0;
         return tree_bytes(N) + kXchgBytes + x + t;
     }
     __host__ __device__ static size_t gbytes(int N) {                     // global scratch bytes per warp (tree + channel rows)
@@ -149,8 +157,9 @@ struct WarpMem {
     __device__ void carve(unsigned char* sbase, unsigned char* gbase, int N, int xk = 0, unsigned char* hbase = nullptr) {
         ts = reinterpret_cast<float*>(sbase);
         xchg = reinterpret_cast<unsigned long long*>(sbase + tree_bytes(N));
-        absl = reinterpret_cast<float*>(sbase + tree_bytes(N) + kXchgBytes);
-        lin = sbase + bytes(N, xk, 0);
+        absl = absl_aliases_tree(N, xk) ? reinterpret_cast<float*>(sbase + stash_bytes(N))
+                                        : reinterpret_cast<float*>(sbase + tree_bytes(N) + kXchgBytes);
+        lin = reinterpret_cast<uint32_t*>(sbase + bytes(N, xk, 0));
         float* g = reinterpret_cast<float*>(gbase);
         tg = g - ((1 << HS) - 2) * 32;
         chan = g + (size_t)tree_rows_global(N, HS) * 32;

@@ -235,7 +235,12 @@ struct ListDecoder {
                         }
                         if constexpr (TRACE) {
                             wm.hist[jinfo * 32 + lane] = L;
-                            wm.lin[jinfo * 32 + lane] = (uint8_t)(src - gbase);
+                            {   // lineage of all 32 lanes as bit planes: three ballots, one 16-byte store
+                                const uint32_t sl = (uint32_t)(src - gbase);
+                                const uint32_t b0 = __ballot_sync(kFull, sl & 1u), b1 = __ballot_sync(kFull, sl & 2u);
+                                const uint32_t b2 = MP > 4 ? __ballot_sync(kFull, sl & 4u) : 0u;
+                                if (lane == 0) *reinterpret_cast<uint4*>(wm.lin + jinfo * 4) = make_uint4(b0, b1, b2, 0u);
+                            }
                             ++jinfo;
                         }
                         // The second child of a doubly-surviving path moves into a freed slot.  Every lane reads from
@@ -336,7 +341,11 @@ struct ListDecoder {
                 const int j = jtop - t;
                 if (j >= 0) {
                     int w = 0;
-                    if constexpr (MP > 1) w = wm.lin[j * 32 + gbase + s];
+                    if constexpr (MP > 1) {
+                        const uint4 q = *reinterpret_cast<const uint4*>(wm.lin + j * 4);      // broadcast read
+                        const int sh = gbase + s;
+                        w = (int)(((q.x >> sh) & 1u) | (((q.y >> sh) & 1u) << 1) | (((q.z >> sh) & 1u) << 2));
+                    }
                     if ((j & (MP - 1)) == slot) mine = (mine << 4) | (unsigned long long)w;
                     s = w;
                 }

@@ -4,12 +4,13 @@
 // Reference paths: eval/run_fer_sweep.py:60-121 (channel, counters), eval/run_ber_sweep.py:112-181,
 // dlscl/flip.py:65-141 (retry controller), nr/polar/scl_nr.py:23-57 (rate-matched chain).
 //
-// DL-SCL on the GPU: the baseline pass decodes every frame; frames whose best path fails the CRC are appended to
-// a queue (frame id, best u-hat, transmitted word, their LLR row goes to the LLR store).  ONE persistent retry
-// kernel then drains the queue: every lane group owns a frame through all of its retries -- replay the reference
-// path to get |L0| (flip.py:102,133), score q = |L0| @ beta in fp64 (flip.py:104-108), force the prefix + flipped
-// bit (flip.py:30-34), list-decode, finish or go on -- and pulls the next entry when its frame is done, so all
-// lanes stay busy whatever the SNR and nothing is regenerated or re-queued between retries.
+// DL-SCL on the GPU: the baseline pass decodes every frame and records the leaf-LLR trace; frames whose best path
+// fails the CRC are appended to a queue (frame id, best u-hat, transmitted word; their LLR row goes to the LLR store,
+// the |L0| vector of their best path -- read off the trace -- to the |L0| store).  ONE persistent retry kernel then
+// drains the queue: every lane group owns a frame through all of its retries -- score q = |L0| @ beta in fp64
+// (flip.py:104-108), force the prefix + flipped bit (flip.py:30-34), list-decode with the trace on, finish or walk
+// the trace for the next |L0| (flip.py:102,133) and go on -- and pulls the next entry when its frame is done, so all
+// lanes stay busy whatever the SNR and nothing is regenerated, replayed or re-queued between retries.
 #pragma once
 #include "polar_kernels.cuh"
 
@@ -113,7 +114,7 @@ enum { cFrames = 0, cSclFe, cSclBe, cDlFe, cDlBe, cUncFe, cUncBe, cDlWork, cNear
 // bit-error count.  Scratch: the (not yet used) tree area.
 // ---------------------------------------------------------------------------------------------------
 #ifndef PB_RETRY_THREADS
-#define PB_RETRY_THREADS 768
+#define PB_RETRY_THREADS 1024
 #endif
 #ifndef PB_SWEEP_THREADS
 #define PB_SWEEP_THREADS 1024

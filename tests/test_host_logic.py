@@ -226,3 +226,12 @@ def test_ldpc_h_matrix_host_side(gldpc):
         load_base_graph(7)
     with pytest.raises(ValueError):
         build_h_matrix(2, 0)
+
+
+def test_numa_binding_is_best_effort():
+    """bind_to_gpu_numa must never raise: no CUDA device / no sysfs PCI tree -> None, affinity untouched."""
+    from polar_code_b200.montecarlo import bind_to_gpu_numa
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa(0) is None or isinstance(bind_to_gpu_numa(0), str)
+    if not torch.cuda.is_available():
+        assert os.sched_getaffinity(0) == before
