@@ -113,6 +113,7 @@ struct pb200_engine {
     uint32_t* d_info_mask = nullptr;
     uint32_t* d_crc_tab = nullptr;
     int16_t* d_rm_src = nullptr;
+    int8_t* d_rm_cnt = nullptr;
     int16_t* d_tx_src = nullptr;   // NR transmit gather: tx[e] = code[tx_src[e]] or pad (-1)
     std::map<int, uint32_t*> enc_tabs;   // sweep encoder tables, one per payload length (polar_abi_sweep.inl get_enc_tab)
     std::map<std::tuple<int, int, int>, KernelCfg> cfg_cache;
@@ -222,6 +223,7 @@ extern "C" int pb200_create(pb200_engine** out, int device, int N, const int32_t
     }
     std::vector<int16_t> rm(N);
     for (int i = 0; i < N; ++i) rm[i] = (int16_t)i;
+    std::vector<int8_t> rc1(N, 1);
     auto up = [&](void** d, const void* h, size_t bytes) -> cudaError_t {
         cudaError_t r = cudaMalloc(d, bytes);
         if (r != cudaSuccess) return r;
@@ -231,7 +233,8 @@ extern "C" int pb200_create(pb200_engine** out, int device, int N, const int32_t
     if ((ce = up((void**)&e->d_info_pos, pos16.data(), pos16.size() * 2)) != cudaSuccess ||
         (ce = up((void**)&e->d_crc_tab, crc_tab.data(), crc_tab.size() * 4)) != cudaSuccess ||
         (ce = up((void**)&e->d_info_mask, e->code.info_mask, sizeof e->code.info_mask)) != cudaSuccess ||
-        (ce = up((void**)&e->d_rm_src, rm.data(), rm.size() * 2)) != cudaSuccess) {
+        (ce = up((void**)&e->d_rm_src, rm.data(), rm.size() * 2)) != cudaSuccess ||
+        (ce = up((void**)&e->d_rm_cnt, rc1.data(), rc1.size())) != cudaSuccess) {
         pb200_destroy(e);
         return fail(PB200_ECUDA, "table upload failed: %s", cudaGetErrorString(ce));
     }
@@ -239,6 +242,7 @@ extern "C" int pb200_create(pb200_engine** out, int device, int N, const int32_t
     e->tb.info_mask = e->d_info_mask;
     e->tb.crc_tab = e->d_crc_tab;
     e->tb.rm_src = e->d_rm_src;
+    e->tb.rm_cnt = e->d_rm_cnt;
     e->tb.E = 0;
     int rc = sweep_build_tables(e);
     if (rc) { pb200_destroy(e); return rc; }
@@ -249,7 +253,7 @@ extern "C" int pb200_create(pb200_engine** out, int device, int N, const int32_t
 extern "C" void pb200_destroy(pb200_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
-    cudaFree(e->d_info_pos); cudaFree(e->d_info_mask); cudaFree(e->d_crc_tab); cudaFree(e->d_rm_src); cudaFree(e->d_tx_src);
+    cudaFree(e->d_info_pos); cudaFree(e->d_info_mask); cudaFree(e->d_crc_tab); cudaFree(e->d_rm_src); cudaFree(e->d_rm_cnt); cudaFree(e->d_tx_src);
     for (auto& kv : e->enc_tabs) cudaFree(kv.second);
     cudaFree(e->d_llr_store); cudaFree(e->d_abs_store); cudaFree(e->d_rm_dst);
     for (auto& kv : e->scratch) cudaFree(kv.second.first); cudaFree(e->d_q[0]); cudaFree(e->d_q[1]); cudaFree(e->d_q_counts);
@@ -269,6 +273,7 @@ extern "C" int pb200_set_rate_matching(pb200_engine* e, int E) {
     cudaFree(e->d_tx_src);
     e->d_tx_src = nullptr;
     std::vector<int16_t> rm(N), rd(N);
+    std::vector<int8_t> rcnt(N, 1);
     if (E == 0) {
         for (int i = 0; i < N; ++i) { rm[i] = (int16_t)i; rd[i] = (int16_t)i; }
     } else {
@@ -278,6 +283,13 @@ extern "C" int pb200_set_rate_matching(pb200_engine* e, int E) {
         for (int i = 0; i < total; ++i) inv[order[i]] = i;                           // argsort(order), :31-36
         // receive side: internal[i] = derated[inv[i]] if inv[i] < N else 0.0 (zero padding, :33-34)
         for (int i = 0; i < N; ++i) rm[i] = (int16_t)(inv[i] < N ? inv[i] : -1);
+        // copies of de-rate-matched position p = rm[i] among the E transmitted symbols (rate_match.py:19-39)
+        for (int i = 0; i < N; ++i) {
+            const int pp = rm[i];
+            const int copies = pp < 0 ? -1 : (pp < E ? (E - pp + N - 1) / N : 0);
+            if (copies > 127) return fail(PB200_ENOSUP, "E > 127 N is not supported");
+            rcnt[i] = (int8_t)copies;
+        }
         for (int p = 0; p < N; ++p) rd[p] = (int16_t)(order[p] < N ? order[p] : -1);
         // transmit side: interleaved[k] = code[order[k]] or pad -1 (:17-21); rate_match: first E of the tiling (:8-16)
         std::vector<int16_t> tx(E);
@@ -290,6 +302,7 @@ extern "C" int pb200_set_rate_matching(pb200_engine* e, int E) {
     }
     CUDA_TRY(cudaMemcpy(e->d_rm_src, rm.data(), (size_t)N * 2, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(e->d_rm_dst, rd.data(), (size_t)N * 2, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(e->d_rm_cnt, rcnt.data(), (size_t)N, cudaMemcpyHostToDevice));
     e->tb.E = E;
     return PB200_OK;
 }

@@ -89,6 +89,7 @@ static int fill_chan(pb200_engine* e, const pb200_sweep_cfg* c, ChanCfg* cc) {
     cc->deg = e->code.crc_deg;
     cc->tx_src = e->d_tx_src;
     cc->rm_dst = e->d_rm_dst;
+    cc->has_pads = (e->tb.E != 0 && (e->code.N % 32) != 0) ? 1 : 0;
     return get_enc_tab(e, c->k_payload, &cc->enc_tab);
 }
 

@@ -10,6 +10,7 @@ struct Tables {
     const uint32_t* info_mask;   // [16] device copy of Code::info_mask for dynamic indexing
     const uint32_t* crc_tab;     // [N/4][16] syndrome contribution of nibble value v at nibble position p
     const int16_t* rm_src;       // [N] NR: position in the de-rate-matched vector feeding internal LLR i, -1 = 0.0
+    const int8_t* rm_cnt;        // [N] NR: number of transmitted copies combined into internal LLR i; 0 = never sent (-1.0), -1 = pad (0.0)
     int E;                       // NR transmitted length (0 = off)
 };
 

@@ -59,6 +59,7 @@ struct ChanCfg {
     const uint32_t* enc_tab;   // [ceil(kp/4)][16][XW] u-word contribution of payload nibble q with value v (CRC bits included)
     const int16_t* tx_src;     // [E] NR transmit gather (code index or -1 = pad symbol +3)
     const int16_t* rm_dst;     // [N] NR: internal index fed by de-rate-matched position p (-1 none)
+    int has_pads;              // NR: some internal positions are fed by interleaver pads (N not a multiple of 32)
 };
 
 struct DlEntryHdr { long long frame; uint32_t flags; uint32_t n_tried; };
@@ -229,31 +230,33 @@ __device__ __forceinline__ void gen_channel(const Code& code, const Tables& tb, 
     const bool nr = tb.E != 0;
     const int Eeff = nr ? tb.E : N;
     const int nblk = N >= 4 ? N / 4 : 1;
-    if (nr && !raw_out) {
-        for (int e = lane; e < FPW * N; e += 32) wm.chan[(e >> code.n) * chan_stride(N) + (e & (N - 1))] = 0.f;
-        __syncwarp();
-    }
     const int rounds = (Eeff + N - 1) / N;
     const int lg_nblk = code.n >= 2 ? code.n - 2 : 0;            // nblk = 2^lg_nblk
-    for (int k = 0; k < rounds; ++k) {
-        for (int item = lane; item < FPW * nblk; item += 32) {
-            const int f = item >> lg_nblk, jb = item & (nblk - 1);
-            const long long fr = fids[f];
-            if (fr < 0) continue;
+    for (int item = lane; item < FPW * nblk; item += 32) {
+        const int f = item >> lg_nblk, jb = item & (nblk - 1);
+        const long long fr = fids[f];
+        if (fr < 0) continue;
+        if (!nr && N >= 4) {
+            // plain mother code: the four symbols of this block are four neighbouring codeword bits
+            float z[4];
+            normal4(philox4x32_10(make_uint4((uint32_t)fr, (uint32_t)(fr >> 32), (uint32_t)jb, kPurposeNoise), key), z);
+            const uint32_t nib = (scr[(R2 + (jb >> 3)) * 32 + f * MP] >> ((jb & 7) * 4)) & 15u;
+            float4 v;
+            v.x = fmaf(cc.sigma, z[0], 1.0f - 2.0f * (float)(nib & 1u)) * cc.scale;
+            v.y = fmaf(cc.sigma, z[1], 1.0f - 2.0f * (float)((nib >> 1) & 1u)) * cc.scale;
+            v.z = fmaf(cc.sigma, z[2], 1.0f - 2.0f * (float)((nib >> 2) & 1u)) * cc.scale;
+            v.w = fmaf(cc.sigma, z[3], 1.0f - 2.0f * (float)((nib >> 3) & 1u)) * cc.scale;
+            if (raw_out) *reinterpret_cast<float4*>(raw_out + (fr - raw_base) * (long long)N + jb * 4) = v;
+            else *reinterpret_cast<float4*>(wm.chan + f * chan_stride(N) + jb * 4) = v;
+            continue;
+        }
+        // general path (NR rate matching, N = 2): this lane owns the positions p = 4 jb + c of EVERY repetition round,
+        // so the copies of a position are summed in registers, round by round (= the order of load_channel), and
+        // the mean is stored once (rate_match.py:19-39 + interleaver.py:26-37)
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < rounds; ++k) {
             float z[4];
             normal4(philox4x32_10(make_uint4((uint32_t)fr, (uint32_t)(fr >> 32), (uint32_t)(k * nblk + jb), kPurposeNoise), key), z);
-            if (!nr && N >= 4) {
-                // plain mother code: the four symbols of this block are four neighbouring codeword bits
-                const uint32_t nib = (scr[(R2 + (jb >> 3)) * 32 + f * MP] >> ((jb & 7) * 4)) & 15u;
-                float4 v;
-                v.x = fmaf(cc.sigma, z[0], 1.0f - 2.0f * (float)(nib & 1u)) * cc.scale;
-                v.y = fmaf(cc.sigma, z[1], 1.0f - 2.0f * (float)((nib >> 1) & 1u)) * cc.scale;
-                v.z = fmaf(cc.sigma, z[2], 1.0f - 2.0f * (float)((nib >> 2) & 1u)) * cc.scale;
-                v.w = fmaf(cc.sigma, z[3], 1.0f - 2.0f * (float)((nib >> 3) & 1u)) * cc.scale;
-                if (raw_out) *reinterpret_cast<float4*>(raw_out + (fr - raw_base) * (long long)N + jb * 4) = v;
-                else *reinterpret_cast<float4*>(wm.chan + f * chan_stride(N) + jb * 4) = v;
-                continue;
-            }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int p = jb * 4 + c;          // position inside this round
@@ -264,26 +267,30 @@ __device__ __forceinline__ void gen_channel(const Code& code, const Tables& tb, 
                     if (src >= 0) s = 1.0f - 2.0f * (float)((scr[(R2 + (src >> 5)) * 32 + f * MP] >> (src & 31)) & 1u);
                     const float llr = fmaf(cc.sigma, z[c], s) * cc.scale;
                     if (raw_out) raw_out[(fr - raw_base) * (long long)Eeff + t] = llr;
-                    else if (!nr) wm.chan[f * chan_stride(N) + t] = llr;
-                    else {
-                        const int dst = __ldg(&cc.rm_dst[p]);
-                        if (dst >= 0) wm.chan[f * chan_stride(N) + dst] += llr;   // k ascending = the order of load_channel
+                    acc[c] = k == 0 ? llr : acc[c] + llr;
+                }
+            }
+        }
+        if (!raw_out) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int p = jb * 4 + c;
+                if (p < N) {
+                    const int dst = nr ? (int)__ldg(&cc.rm_dst[p]) : p;
+                    if (dst >= 0) {
+                        const int cnt = nr ? (int)__ldg(&tb.rm_cnt[dst]) : 1;
+                        wm.chan[f * chan_stride(N) + dst] = cnt == 0 ? -1.0f : (cnt == 1 ? acc[c] : acc[c] / (float)cnt);
                     }
                 }
             }
         }
-        __syncwarp();
     }
-    if (nr && !raw_out) {
+    __syncwarp();
+    if (nr && !raw_out && cc.has_pads) {
+        // internal positions fed by an interleaver pad carry 0.0 (interleaver.py:33-34)
         for (int e = lane; e < FPW * N; e += 32) {
             const int f = e >> code.n, i = e & (N - 1);
-            const int p = tb.rm_src[i];
-            float v = 0.f;
-            if (p >= 0) {
-                const int cnt = p < Eeff ? (Eeff - p + N - 1) / N : 0;
-                v = cnt ? wm.chan[f * chan_stride(N) + i] / (float)cnt : -1.0f;
-            }
-            wm.chan[f * chan_stride(N) + i] = v;
+            if (fids[f] >= 0 && __ldg(&tb.rm_cnt[i]) < 0) wm.chan[f * chan_stride(N) + i] = 0.f;
         }
         __syncwarp();
     }
