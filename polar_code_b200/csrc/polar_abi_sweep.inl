@@ -130,9 +130,19 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
         rgrid = std::max(1, e->sms * kr.ctas_per_sm);
     }
     const int fpw = 32 / MP;
-    // pieces of 4 Mi frames: with retries every queued frame keeps its LLR row (N floats) in the store, so the
+    // pieces of >= 4 Mi frames: with retries every queued frame keeps its LLR row (N floats) in the store, so the
     // worst case (every frame fails) is 4 Mi x N x 4 B = 2 GB for N = 128 -- allocated lazily, grown on demand
-    const long long piece_max = 1ll << 22;
+    // With retries every piece ends in a tail in which the last frames run their (sequential) retries on a mostly idle
+    // GPU, so DL-SCL pieces are made as large as memory comfortably allows: up to 16 Mi frames (14 GB of queue, LLR and
+    // |L0| stores for N = 128 -- a B200 has 180 GB), less when less than four times that is free.
+    long long piece_max = 1ll << 22;
+    if (a.retries > 0) {
+        const size_t per_frame = (size_t)code.N * 4 + (size_t)code.K * 4 + entry_bytes(e);
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
+        const size_t have = free_b + e->llr_store_bytes + e->abs_store_bytes + e->q_bytes;    // what we hold already counts
+        while (piece_max < (1ll << 24) && (size_t)(piece_max * 2) * per_frame * 4 <= have) piece_max *= 2;
+    }
     const long long total = a.n_frames, begin0 = a.frame_begin;
     const long long out_base = a.frame_begin;   // per-frame outputs are indexed by frame - frame_begin of the whole call
     (void)out_base;

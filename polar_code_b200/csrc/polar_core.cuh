@@ -125,19 +125,25 @@ struct WarpMem {
                           // from at info phase j (shared; written by lane 0)
     float* hist;          // [K][32] trace mode only: leaf LLR every slot saw at info phase j (global scratch)
     static constexpr int FPW = 32 / MP;
-    __host__ __device__ static size_t tree_bytes(int N) { return (size_t)tree_rows_shared(N, HS) * 32 * 4; }
+    // Shared layout of a warp, all offsets compile-time constants (the hot loop re-derives these pointers from the warp
+    // base whenever registers are short -- with N-dependent sizes that re-derivation was ~8 % of all instructions):
+    //   [0, kTreeBytes) tree rows of heights < HS (always the full 2^HS - 2 rows)   [kTreeBytes, +kXchgBytes) xchg
+    //   then the lineage words (trace kernels), then the |L0| rows unless they alias the tree area
+    static constexpr int kTreeRows = (1 << HS) - 2;
+    static constexpr size_t kTreeBytes = (size_t)kTreeRows * 32 * 4;
+    __host__ __device__ static size_t tree_bytes(int) { return kTreeBytes; }
+    __host__ __device__ static size_t lin_bytes(int tk) { return (tk && MP > 1) ? (size_t)tk * 16 : 0; }
     // The |L0| rows of the DL-SCL retry kernel are only live BETWEEN two list decodes (trace walk -> beta scoring), when
     // the tree rows are dead: they alias the shared tree area behind the stash rows whenever they fit there.
     __host__ __device__ static size_t absl_bytes(int xk) { return xk ? (((size_t)FPW * (xk + 1) * 4 + 15) & ~(size_t)15) : 0; }
     __host__ __device__ static size_t stash_bytes(int N) { return (size_t)3 * (N >= 32 ? N / 32 : 1) * 32 * 4; }
     __host__ __device__ static bool absl_aliases_tree(int N, int xk) {
-        return xk && tree_rows_shared(N, HS) * 32 * 4 >= (int)(stash_bytes(N) + absl_bytes(xk));
+        return xk && kTreeBytes >= stash_bytes(N) + absl_bytes(xk);
     }
     // shared bytes per warp: xk > 0 adds the |L0| rows, tk > 0 the lineage words of the trace (info_llrs without a replay)
     __host__ __device__ static size_t bytes(int N, int xk = 0, int tk = 0) {
         size_t x = absl_aliases_tree(N, xk) ? 0 : absl_bytes(xk);
-        size_t t = (tk && MP > 1) ? (size_t)tk * 16 : 0;
-        return tree_bytes(N) + kXchgBytes + x + t;
+        return kTreeBytes + kXchgBytes + lin_bytes(tk) + x;
     }
     __host__ __device__ static size_t gbytes(int N) {                     // global scratch bytes per warp (tree + channel rows)
         size_t t = (size_t)tree_rows_global(N, HS) * 32 * 4;
@@ -154,18 +160,18 @@ struct WarpMem {
         const size_t warps = (size_t)gridDim.x * (blockDim.x >> 5);
         return scratch + warps * gbytes(N) + ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * hbytes(K);
     }
-    __device__ void carve(unsigned char* sbase, unsigned char* gbase, int N, int xk = 0, unsigned char* hbase = nullptr) {
+    __device__ void carve(unsigned char* sbase, unsigned char* gbase, int N, int xk = 0, unsigned char* hbase = nullptr, int tk = 0) {
         ts = reinterpret_cast<float*>(sbase);
-        xchg = reinterpret_cast<unsigned long long*>(sbase + tree_bytes(N));
+        xchg = reinterpret_cast<unsigned long long*>(sbase + kTreeBytes);
+        lin = reinterpret_cast<uint32_t*>(sbase + kTreeBytes + kXchgBytes);
         absl = absl_aliases_tree(N, xk) ? reinterpret_cast<float*>(sbase + stash_bytes(N))
-                                        : reinterpret_cast<float*>(sbase + tree_bytes(N) + kXchgBytes);
-        lin = reinterpret_cast<uint32_t*>(sbase + bytes(N, xk, 0));
+                                        : reinterpret_cast<float*>(sbase + kTreeBytes + kXchgBytes + lin_bytes(tk));
         float* g = reinterpret_cast<float*>(gbase);
         tg = g - ((1 << HS) - 2) * 32;
         chan = g + (size_t)tree_rows_global(N, HS) * 32;
         hist = reinterpret_cast<float*>(hbase);
         const int need = 3 * (N >= 32 ? N / 32 : 1);
-        scr = (tree_rows_shared(N, HS) >= need) ? ts : g;
+        scr = (kTreeRows >= need) ? ts : g;
     }
 };
 

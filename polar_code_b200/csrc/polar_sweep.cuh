@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(PB_SWEEP_THREADS) sweep_kernel(const Code code
     WM wm;
     const size_t kWarpBytes = WM::bytes(code.N, 0, TRACE ? code.K : 0);
     wm.carve(smem + (size_t)warp * kWarpBytes, WM::warp_scratch(a.gscratch, code.N), code.N, 0,
-             TRACE ? WM::warp_trace(a.gscratch, code.N, code.K) : nullptr);
+             TRACE ? WM::warp_trace(a.gscratch, code.N, code.K) : nullptr, TRACE ? code.K : 0);
     const bool leader = (lane & (MP - 1)) == 0;
     static_assert(cNum <= 12, "counter column");
     const AccRef acc{reinterpret_cast<uint32_t*>(smem + (size_t)wpc * kWarpBytes + (size_t)warp * acc_bytes(MP)) + lane / MP, FPW};
@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(PB_SWEEP_THREADS) sweep_kernel(const Code code
 // LLRs are never recomputed by an SC replay.
 // ---------------------------------------------------------------------------------------------------
 template <int MP, int LOGMAX, int HS = 5>
-__global__ void __launch_bounds__(PB_RETRY_THREADS) dl_retry_kernel(const Code code, const Tables tb, const SweepArgs a) {
+__global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_retry_kernel(const Code code, const Tables tb, const SweepArgs a) {
     using S = Sweep<MP, LOGMAX, HS>;
     using WM = WarpMem<MP, HS>;
     using PathT = typename S::PathT;
@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(PB_RETRY_THREADS) dl_retry_kernel(const Code c
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     WM wm;
     const size_t kWarpBytes = WM::bytes(code.N, code.K, code.K);
-    wm.carve(smem + (size_t)warp * kWarpBytes, WM::warp_scratch(a.gscratch, code.N), code.N, code.K, WM::warp_trace(a.gscratch, code.N, code.K));
+    wm.carve(smem + (size_t)warp * kWarpBytes, WM::warp_scratch(a.gscratch, code.N), code.N, code.K, WM::warp_trace(a.gscratch, code.N, code.K), code.K);
     const int slot = lane & (MP - 1), fme = lane / MP, gbase = lane & ~(MP - 1);
     float* ab = wm.absl + fme * (code.K + 1);      // |L0| of the reference path of this group's frame
     const bool leader = slot == 0;

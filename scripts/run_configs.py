@@ -13,6 +13,8 @@ def run(name, argv):
     tail = (out.stdout.strip().splitlines() or [""])[-3:]
     print(f"== {name}: {dt:.2f} s wall (rc={out.returncode})")
     for l in tail: print("   ", l[:160])
+    for l in out.stderr.splitlines():
+        if l.startswith("[b200]"): print("   ", l)
     if out.returncode: print(out.stderr[-800:])
 
 F = "dl_scl_polar.eval.run_fer_sweep"; B = "dl_scl_polar.eval.run_ber_sweep"
@@ -23,3 +25,5 @@ run("config3: DL-SCL M=4 r8 beta_M4, 1e7 frames/point, 4.0-6.5 dB", [F, "--M", "
 run("config4: NR E=256 M=4 BER sweep 1.0-6.5 dB", [B, "--scheme", "nr_polar_scl", "--K_payload", "64", "--K_crc", "24", "--N", "128", "--E", "256", "--M", "4",
      "--EbN0_lo", "1.0", "--EbN0_hi", "6.5", "--EbN0_step", "0.5", "--bits_cap", "1e7", "--err_cap", "1000", "--out", "gpurun_out/c4/nr.csv"])
 run("config5 (1 GPU slice): DL-SCL M=8 r8 beta_M8, 1e8 frames at 5.0 dB", [F, "--M", "8", "--frames", "100000000", "--snr_lo", "5.0", "--snr_step", "0", "--beta", "gpurun_out/beta_M8.npy", "--out_dir", "gpurun_out/c5", "--plot_dir", "gpurun_out/c5"])
+run("ldpc: run_ber_sweep --scheme nr_ldpc bg 2 Z 32 (K_payload 72 + CRC-24), E = 384, 1.0-3.0 dB", [B, "--scheme", "nr_ldpc", "--K_payload", "72", "--K_crc", "24", "--E", "384",
+     "--bg", "2", "--Z", "32", "--EbN0_lo", "1.0", "--EbN0_hi", "3.0", "--EbN0_step", "1.0", "--bits_cap", "1e7", "--err_cap", "1000", "--out", "gpurun_out/c6/ldpc.csv"])
