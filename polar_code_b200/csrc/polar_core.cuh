@@ -60,6 +60,11 @@ __device__ __forceinline__ float g_op(float a, float b, uint32_t bit) {
     // polar.py:126-127 : b + (1-2c) a
     return b + __uint_as_float(__float_as_uint(a) ^ (bit << 31));
 }
+// The same with the partial-sum bit taken straight from its packed word: bit `pos` of `word` is moved onto the sign
+// position (one shift), masked and XOR-ed into a in one LOP3 -- three instructions per g instead of five.
+__device__ __forceinline__ float g_op_packed(float a, float b, uint32_t word, int pos) {
+    return b + __uint_as_float(__float_as_uint(a) ^ ((word << (31 - pos)) & 0x80000000u));
+}
 
 // log(1+exp(-|L|)) -- the part both softplus branches share (scl.py:102-105; numpy logaddexp = max + log1p(exp(-|d|))).
 // t = exp(-|L|) in (0,1]; log1p(t) = t*q(t) with q a degree-9 near-minimax polynomial of log1p(t)/t on [0,1]
@@ -188,6 +193,11 @@ __device__ __forceinline__ uint32_t left_bit(const uint32_t (&bw)[BW], int i) {
     if constexpr (H < 5) return (bw[0] >> (((1 << H) - 1) + i)) & 1u;
     else return 0;  // H >= 5 handled word-wise by the callers
 }
+// g with bit i of the left-child buffer at height H < 5 (static position in word 0)
+template <int H, int BW>
+__device__ __forceinline__ float g_left(float a, float b, const uint32_t (&bw)[BW], int i) {
+    return g_op_packed(a, b, bw[0], ((1 << H) - 1) + i);
+}
 
 // Upward propagation after deciding `bit` at a phase with T trailing ones
 // (scl.py:84-99).  cur (2^T bits) is returned in cw[]; the caller stores it as
@@ -308,11 +318,11 @@ struct Tree {
     // bit e of the left-child buffer of height H (H in 4..6), for e = g + G*k with runtime g < G = 2^H/8 and
     // static k: the word index depends on k only, so every register index stays static.
     template <int H, int K>
-    static __device__ __forceinline__ uint32_t strided_bit(const uint32_t (&bw)[BW], int g) {
+    static __device__ __forceinline__ float g_strided(float a, float b, const uint32_t (&bw)[BW], int g) {
         constexpr int G = (1 << H) / 8;
-        if constexpr (H == 4) return (bw[0] >> (15 + g + G * K)) & 1u;
-        else if constexpr (H == 5) return (bw[1] >> (g + G * K)) & 1u;
-        else return (bw[2 + (K >= 4 ? 1 : 0)] >> (g + G * (K & 3))) & 1u;     // H == 6: e < 32 iff K < 4
+        if constexpr (H == 4) return g_op_packed(a, b, bw[0], 15 + g + G * K);
+        else if constexpr (H == 5) return g_op_packed(a, b, bw[1], g + G * K);
+        else return g_op_packed(a, b, bw[2 + (K >= 4 ? 1 : 0)], g + G * (K & 3));     // H == 6: e < 32 iff K < 4
     }
 
     // Produce height H (>= 1) from height H+1 held at src[i*STRIDE] (STRIDE 32: a tree slot, lane folded into src;
@@ -333,7 +343,7 @@ struct Tree {
 #pragma unroll
             for (int i = 0; i < S; ++i) {
                 const float x = src[i * STRIDE], y = src[(i + S) * STRIDE];
-                v[i] = OP ? g_op(x, y, left_bit<H, BW>(bw, i)) : f_op(x, y);
+                v[i] = OP ? g_left<H, BW>(x, y, bw, i) : f_op(x, y);
                 if constexpr (H >= 2) own[((S - 2) + i) * 32] = v[i];
             }
             reg_chain<H>(v, wm, lane, a, b);
@@ -347,14 +357,14 @@ struct Tree {
             // one group = the 8 strided elements {g + G*k}: reduce them to heights H-1, H-2, H-3 in registers
             auto group = [&](int g, const float (&x)[8], const float (&y)[8]) {
                 float v[8];
-                v[0] = OP ? g_op(x[0], y[0], strided_bit<H, 0>(bw, g)) : f_op(x[0], y[0]);
-                v[1] = OP ? g_op(x[1], y[1], strided_bit<H, 1>(bw, g)) : f_op(x[1], y[1]);
-                v[2] = OP ? g_op(x[2], y[2], strided_bit<H, 2>(bw, g)) : f_op(x[2], y[2]);
-                v[3] = OP ? g_op(x[3], y[3], strided_bit<H, 3>(bw, g)) : f_op(x[3], y[3]);
-                v[4] = OP ? g_op(x[4], y[4], strided_bit<H, 4>(bw, g)) : f_op(x[4], y[4]);
-                v[5] = OP ? g_op(x[5], y[5], strided_bit<H, 5>(bw, g)) : f_op(x[5], y[5]);
-                v[6] = OP ? g_op(x[6], y[6], strided_bit<H, 6>(bw, g)) : f_op(x[6], y[6]);
-                v[7] = OP ? g_op(x[7], y[7], strided_bit<H, 7>(bw, g)) : f_op(x[7], y[7]);
+                v[0] = OP ? g_strided<H, 0>(x[0], y[0], bw, g) : f_op(x[0], y[0]);
+                v[1] = OP ? g_strided<H, 1>(x[1], y[1], bw, g) : f_op(x[1], y[1]);
+                v[2] = OP ? g_strided<H, 2>(x[2], y[2], bw, g) : f_op(x[2], y[2]);
+                v[3] = OP ? g_strided<H, 3>(x[3], y[3], bw, g) : f_op(x[3], y[3]);
+                v[4] = OP ? g_strided<H, 4>(x[4], y[4], bw, g) : f_op(x[4], y[4]);
+                v[5] = OP ? g_strided<H, 5>(x[5], y[5], bw, g) : f_op(x[5], y[5]);
+                v[6] = OP ? g_strided<H, 6>(x[6], y[6], bw, g) : f_op(x[6], y[6]);
+                v[7] = OP ? g_strided<H, 7>(x[7], y[7], bw, g) : f_op(x[7], y[7]);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) o0[(g + G * k) * 32] = v[k];
                 float w[4], z[2];
@@ -402,7 +412,7 @@ struct Tree {
                 for (int j = 0; j < 32; ++j) {
                     const int i = w * 32 + j;
                     const float x = src[i * STRIDE], y = src[(i + S) * STRIDE];
-                    dst[i * 32] = OP ? g_op(x, y, (bits >> j) & 1u) : f_op(x, y);
+                    dst[i * 32] = OP ? g_op_packed(x, y, bits, j) : f_op(x, y);
                 }
             }
             produce<H - 1, 0, 32>(dst, bw, wm, lane, a, b);

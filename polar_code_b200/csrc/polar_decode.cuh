@@ -158,7 +158,7 @@ struct ListDecoder {
                 } else pair_llr<R == 2>(code, wm, p, phi, lane, chanf, a, b);
                 L = f_op(a, b);
             }
-            else L = g_op(a, b, p.bw[0] & 1u);                   // u_{phi-1} sits in the height-0 field
+            else L = g_op_packed(a, b, p.bw[0], 0);              // u_{phi-1} sits in the height-0 field
             const bool is_info = (cur_info >> (phi & 31)) & 1u;
             const bool is_forced = FORCED && is_info && ((cur_fm >> (phi & 31)) & 1u);
             const uint32_t forced_val = (cur_fv >> (phi & 31)) & 1u;
@@ -388,7 +388,7 @@ struct ListDecoder {
             const bool odd = phi & 1;
             float L;
             if (!odd) { pair_llr(code, wm, q, phi, lane, chanf, a, b); L = f_op(a, b); }
-            else L = g_op(a, b, q.bw[0] & 1u);
+            else L = g_op_packed(a, b, q.bw[0], 0);
             if ((cur_info >> (phi & 31)) & 1u) { if (active) sink(j, L); ++j; }
             const uint32_t bit = (cur_u >> (phi & 31)) & 1u;
             if (!odd) q.bw[0] = (q.bw[0] & ~1u) | bit;
