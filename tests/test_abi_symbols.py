@@ -35,6 +35,12 @@ def test_no_cpu_fallback():
     import numpy as np
     with pytest.raises(RuntimeError):
         PolarEngine(8, np.array([3, 5, 6, 7], np.int32), None)
+    from polar_code_b200.ldpc import LdpcEngine, build_h_matrix
+    with pytest.raises(RuntimeError):
+        LdpcEngine(build_h_matrix(2, 2))               # building H is host code, running the code is not
+    from polar_code_b200.dl_scl_polar.nr.ldpc import decode_ldpc_nms
+    with pytest.raises(RuntimeError):
+        decode_ldpc_nms(np.zeros(12), build_h_matrix(2, 2))
 
 
 def test_host_side_construction_matches_oracle():
