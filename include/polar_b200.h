@@ -181,6 +181,15 @@ int pb200_ldpc_build_h(int bg, int Z, uint8_t *h_H, int *m, int *n);
 int pb200_ldpc_create(pb200_ldpc **out, int device, const uint8_t *h_H, int m, int n);
 void pb200_ldpc_destroy(pb200_ldpc *e);
 
+/* Host side of the encoder and of the launch planning (no GPU needed; exported so that the host logic is testable
+ * on its own).  parity_generator: the elimination of encode.py:8-49 depends on H only, so parity = G * payload with
+ * h_G[(n-k)][kw] bit rows (kw = max(1, ceil(k/32))); h_C[n_check][kw] are the rows whose non-zero product reproduces
+ * the reference's "Linear system over GF(2) has no solution" (h_G / h_C may be NULL; h_C needs room for m rows).
+ * layers: first row of every layer of consecutive, mutually column-disjoint rows (h_layer_ptr[n_layers+1], room for
+ * m+1), and the lanes per frame of the group-per-frame kernels (0 = thread-per-frame mapping). */
+int pb200_ldpc_parity_generator(const uint8_t *h_H, int m, int n, int k, uint32_t *h_G, uint32_t *h_C, int *n_check);
+int pb200_ldpc_layers(const uint8_t *h_H, int m, int n, int32_t *h_layer_ptr, int *n_layers, int *group_lanes);
+
 /* encode.py:52-66 encode_ldpc: payload[B,k] u8 -> code[B,n] u8 (systematic, parity by GF(2) elimination with free
  * variables 0).  d_status: NULL or u8[B], 1 where the reference raises "Linear system over GF(2) has no solution". */
 int pb200_ldpc_encode_batch(pb200_ldpc *e, const uint8_t *d_payload, int k, uint8_t *d_code, uint8_t *d_status, int64_t B,

@@ -68,6 +68,8 @@ SYMBOLS = {
     "pb200_ldpc_build_h": (C.c_int, [C.c_int, C.c_int, _vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pb200_ldpc_create": (C.c_int, [C.POINTER(_vp), C.c_int, _vp, C.c_int, C.c_int]),
     "pb200_ldpc_destroy": (None, [_vp]),
+    "pb200_ldpc_parity_generator": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, C.POINTER(C.c_int)]),
+    "pb200_ldpc_layers": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pb200_ldpc_encode_batch": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _i64, _vp]),
     "pb200_ldpc_rate_match_batch": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _i64, _vp]),
     "pb200_ldpc_derate_match_batch": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _i64, _vp]),

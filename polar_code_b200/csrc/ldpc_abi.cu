@@ -70,6 +70,42 @@ extern "C" int pb200_ldpc_build_h(int bg, int Z, uint8_t* h_H, int* m_out, int* 
     return PB200_OK;
 }
 
+// Greedy layering of the rows of H: a row joins the current layer while it shares no column with it and the layer has
+// fewer than 32 rows.  lp = first row of every layer (+ m).  lanes = lanes per frame of the group kernels (layer width
+// rounded up to a power of two, 4..32), or 0 when the layers are too narrow (< 4 rows) for that mapping to pay.
+static void build_layers_host(const uint8_t* H, int m, int n, std::vector<int>& lp, int* lanes) {
+    lp.assign(1, 0);
+    std::vector<char> used(n, 0);
+    int width = 0, maxw = 0;
+    for (int r = 0; r < m; ++r) {
+        bool clash = width >= 32;
+        for (int c = 0; c < n && !clash; ++c) clash = H[(size_t)r * n + c] && used[c];
+        if (clash) {
+            lp.push_back(r);
+            std::fill(used.begin(), used.end(), 0);
+            width = 0;
+        }
+        for (int c = 0; c < n; ++c) if (H[(size_t)r * n + c]) used[c] = 1;
+        ++width;
+        maxw = std::max(maxw, width);
+    }
+    lp.push_back(m);
+    int G = 0;
+    if (maxw >= 4) { G = 4; while (G < maxw) G <<= 1; }
+    *lanes = G;
+}
+
+extern "C" int pb200_ldpc_layers(const uint8_t* h_H, int m, int n, int32_t* h_layer_ptr, int* n_layers, int* group_lanes) {
+    if (!h_H || m <= 0 || n <= 0) return lfail(PB200_EINVAL, "H must be a non-empty m x n matrix");
+    std::vector<int> lp;
+    int G = 0;
+    build_layers_host(h_H, m, n, lp, &G);
+    if (h_layer_ptr) for (size_t i = 0; i < lp.size(); ++i) h_layer_ptr[i] = lp[i];
+    if (n_layers) *n_layers = (int)lp.size() - 1;
+    if (group_lanes) *group_lanes = G;
+    return PB200_OK;
+}
+
 extern "C" int pb200_ldpc_create(pb200_ldpc** out, int device, const uint8_t* h_H, int m, int n) {
     if (!out) return lfail(PB200_EINVAL, "out is NULL");
     *out = nullptr;
@@ -103,31 +139,17 @@ extern "C" int pb200_ldpc_create(pb200_ldpc** out, int device, const uint8_t* h_
         pb200_ldpc_destroy(e);
         return lfail(PB200_ECUDA, "table upload failed: %s", cudaGetErrorString(ce));
     }
-    // greedy layering: a row joins the current layer while it shares no column with it (and the layer has < 32 rows)
     {
-        std::vector<int> lp{0};
-        std::vector<char> used(n, 0);
-        int width = 0, maxw = 0;
-        for (int r = 0; r < m; ++r) {
-            bool clash = width >= 32;
-            for (int q = rp[r]; q < rp[r + 1] && !clash; ++q) clash = used[ci[q]] != 0;
-            if (clash) {
-                lp.push_back(r);
-                std::fill(used.begin(), used.end(), 0);
-                width = 0;
-            }
-            for (int q = rp[r]; q < rp[r + 1]; ++q) used[ci[q]] = 1;
-            ++width;
-            maxw = std::max(maxw, width);
-        }
-        lp.push_back(m);
+        std::vector<int> lp;
+        int G = 0;
+        build_layers_host(h_H, m, n, lp, &G);
         e->nl = (int)lp.size() - 1;
         e->weight4 = true;
         for (int r = 0; r < m; ++r) e->weight4 = e->weight4 && (rp[r + 1] - rp[r] == 4);
-        if (maxw >= 4 && e->nnz > 0) {        // narrow layers (Z < 4, unstructured H): one thread per frame is the better mapping
-            int G = 4, lg = 2;
-            while (G < maxw) { G <<= 1; ++lg; }
-            e->G = G; e->lgG = lg;
+        if (G > 0 && e->nnz > 0) {
+            e->G = G;
+            e->lgG = 0;
+            while ((1 << e->lgG) < G) ++e->lgG;
             if ((ce = cudaMalloc((void**)&e->d_layer_ptr, lp.size() * 4)) != cudaSuccess ||
                 (ce = cudaMemcpy(e->d_layer_ptr, lp.data(), lp.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
                 pb200_ldpc_destroy(e);
@@ -153,17 +175,15 @@ extern "C" void pb200_ldpc_destroy(pb200_ldpc* e) {
 // elimination with free variables left at 0 (:8-49); the row operations depend on H_par only, so p = G s with
 // G = rows of (T H_sys) picked by the pivots (T = accumulated row operations), and the "no solution" test
 // (:35-37) is  C s != 0  with C = the rows of T H_sys that belong to the all-zero rows of the reduced matrix.
-static int get_generator(pb200_ldpc* e, int k, const GenDev** out) {
-    auto it = e->gens.find(k);
-    if (it != e->gens.end()) { *out = &it->second; return PB200_OK; }
-    const int m = e->m, n = e->n;
+// host part: G [n-k][kw] and the consistency rows Cc [nc][kw] (kw = max(1, ceil(k/32)))
+static int build_generator_host(const uint8_t* H, int m, int n, int k, std::vector<uint32_t>& G, std::vector<uint32_t>& Cc, int* nc_out) {
     if (k < 0) return lfail(PB200_EINVAL, "payload length must be >= 0");
     if (n <= k) return lfail(PB200_EINVAL, "Parity-check matrix too small for payload length");
     const int np = n - k, kw = std::max(1, (k + 31) / 32), mw = (m + 31) / 32;
     std::vector<std::vector<uint8_t>> A(m, std::vector<uint8_t>(np));
     std::vector<std::vector<uint32_t>> T(m, std::vector<uint32_t>(mw, 0));
     for (int r = 0; r < m; ++r) {
-        for (int c = 0; c < np; ++c) A[r][c] = e->H[(size_t)r * n + k + c] & 1;
+        for (int c = 0; c < np; ++c) A[r][c] = H[(size_t)r * n + k + c] & 1;
         T[r][r >> 5] |= 1u << (r & 31);
     }
     std::vector<int> pivot_row(np, -1);
@@ -187,9 +207,10 @@ static int get_generator(pb200_ldpc* e, int k, const GenDev** out) {
         for (int i = 0; i < m; ++i)
             if ((t[i >> 5] >> (i & 31)) & 1u)
                 for (int j = 0; j < k; ++j)
-                    if (e->H[(size_t)i * n + j] & 1) dst[j >> 5] ^= 1u << (j & 31);
+                    if (H[(size_t)i * n + j] & 1) dst[j >> 5] ^= 1u << (j & 31);
     };
-    std::vector<uint32_t> G((size_t)np * kw, 0), Cc;
+    G.assign((size_t)np * kw, 0);
+    Cc.clear();
     for (int col = 0; col < np; ++col)
         if (pivot_row[col] >= 0) times_hsys(T[pivot_row[col]], &G[(size_t)col * kw]);
     int nc = 0;
@@ -203,6 +224,31 @@ static int get_generator(pb200_ldpc* e, int k, const GenDev** out) {
         for (int w = 0; w < kw; ++w) any = any || tmp[w];
         if (any) { Cc.insert(Cc.end(), tmp.begin(), tmp.end()); ++nc; }
     }
+    *nc_out = nc;
+    return PB200_OK;
+}
+
+extern "C" int pb200_ldpc_parity_generator(const uint8_t* h_H, int m, int n, int k, uint32_t* h_G, uint32_t* h_C, int* n_check) {
+    if (!h_H || m <= 0 || n <= 0) return lfail(PB200_EINVAL, "H must be a non-empty m x n matrix");
+    std::vector<uint32_t> G, Cc;
+    int nc = 0;
+    int rc = build_generator_host(h_H, m, n, k, G, Cc, &nc);
+    if (rc) return rc;
+    if (h_G) memcpy(h_G, G.data(), G.size() * 4);
+    if (h_C && nc) memcpy(h_C, Cc.data(), Cc.size() * 4);
+    if (n_check) *n_check = nc;
+    return PB200_OK;
+}
+
+static int get_generator(pb200_ldpc* e, int k, const GenDev** out) {
+    auto it = e->gens.find(k);
+    if (it != e->gens.end()) { *out = &it->second; return PB200_OK; }
+    const int n = e->n;
+    std::vector<uint32_t> G, Cc;
+    int nc = 0;
+    int rc = build_generator_host(e->H.data(), e->m, n, k, G, Cc, &nc);
+    if (rc) return rc;
+    const int np = n - k, kw = std::max(1, (k + 31) / 32);
     GenDev gd;
     LCUDA_TRY(cudaSetDevice(e->device));
     LCUDA_TRY(cudaMalloc((void**)&gd.d_G, G.size() * 4));

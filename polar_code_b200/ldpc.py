@@ -27,6 +27,32 @@ def build_h_matrix(bg: int, Z: int) -> np.ndarray:
     return H.astype(np.int8)
 
 
+def parity_generator(H, k: int):
+    """Host side of encode.py:52-66: (G, C) with parity = G @ payload (mod 2) and "no solution" iff C @ payload != 0.
+    G: uint8 [n-k, k], C: uint8 [n_check, k]."""
+    lib = L.load()
+    Hu = np.ascontiguousarray(np.asarray(H) % 2, np.uint8)
+    m, n = Hu.shape
+    kw = max(1, (int(k) + 31) // 32)
+    Gw = np.zeros((max(n - int(k), 0), kw), np.uint32)
+    Cw = np.zeros((m, kw), np.uint32)
+    nc = C.c_int()
+    L.check(lib.pb200_ldpc_parity_generator(Hu.ctypes.data, m, n, int(k), Gw.ctypes.data, Cw.ctypes.data, C.byref(nc)))
+    unpack = lambda W: ((W[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(W.shape[0], kw * 32)[:, :int(k)].astype(np.uint8)
+    return unpack(Gw), unpack(Cw[: nc.value])
+
+
+def layers(H):
+    """Host side of the launch planning: (layer_ptr, lanes_per_frame) of the group-per-frame kernels."""
+    lib = L.load()
+    Hu = np.ascontiguousarray(np.asarray(H) % 2, np.uint8)
+    m, n = Hu.shape
+    lp = np.zeros(m + 1, np.int32)
+    nl, g = C.c_int(), C.c_int()
+    L.check(lib.pb200_ldpc_layers(Hu.ctypes.data, m, n, lp.ctypes.data, C.byref(nl), C.byref(g)))
+    return lp[: nl.value + 1].copy(), g.value
+
+
 class LdpcEngine:
     def __init__(self, H, device: int | None = None):
         require_cuda()

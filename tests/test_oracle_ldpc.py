@@ -79,3 +79,59 @@ def test_reference_cli_rows_reproduced(gldpc):
                 err_cap=int(a["--err_cap"]), bits_cap=float(a["--bits_cap"]))
             assert bits == row["bits_total"] and be == row["bit_errors"]
             assert fe / frames == row["fer"] and work / frames == row["avg_work"]
+
+
+# ---- host logic of the product's LDPC path (C-ABI host entry points, no GPU) ------------------------------------
+def test_parity_generator_matches_the_reference_encoder(gldpc):
+    """parity = G * payload reproduces encode_ldpc (oracle, pinned to the reference) for every payload tried,
+    including unit vectors, truncated payload lengths and a rank-deficient parity part."""
+    from polar_code_b200.ldpc import parity_generator
+    rng = np.random.default_rng(9)
+    cases = [(O.ldpc_build_h(2, Z), None) for Z in (2, 4, 8, 32)]
+    Hr = (rng.random((10, 24)) < 0.25).astype(np.int8)
+    Hr[:, 14:] |= np.eye(10, dtype=np.int8)
+    cases += [(Hr, None), (Hr, 9), (O.ldpc_build_h(1, 8), 17)]
+    for H, k in cases:
+        n = H.shape[1]
+        k = n - H.shape[0] if k is None else k
+        G, Cc = parity_generator(H, k)
+        assert G.shape == (n - k, k) and Cc.shape[0] == 0
+        payloads = np.concatenate([np.eye(k, dtype=np.int8), rng.integers(0, 2, (40, k), dtype=np.int8), np.zeros((1, k), np.int8)])
+        for p in payloads:
+            ref = O.ldpc_encode(p, H)
+            assert np.array_equal((G.astype(np.int64) @ p) % 2, ref[k:])
+    # rank-deficient parity part: the consistency rows flag exactly the payloads for which the reference raises
+    Hd = (rng.random((8, 20)) < 0.3).astype(np.int8)
+    Hd[5] = Hd[2]
+    Hd[5, :12] ^= np.array([1, 0, 1] * 4, np.int8)          # same parity part as row 2, different systematic part
+    G, Cc = parity_generator(Hd, 12)
+    assert Cc.shape[0] >= 1
+    seen = set()
+    for p in rng.integers(0, 2, (200, 12), dtype=np.int8):
+        bad = bool(((Cc.astype(np.int64) @ p) % 2).any())
+        try:
+            ref = O.ldpc_encode(p, Hd)
+            assert not bad and np.array_equal((G.astype(np.int64) @ p) % 2, ref[12:])
+        except ValueError:
+            assert bad
+        seen.add(bad)
+    assert seen == {True, False}
+    with pytest.raises(ValueError):
+        parity_generator(O.ldpc_build_h(2, 2), 12)
+
+
+def test_layers_are_column_disjoint_and_cover_all_rows():
+    from polar_code_b200.ldpc import layers
+    rng = np.random.default_rng(4)
+    for H, want_lanes in [(O.ldpc_build_h(2, 2), 0), (O.ldpc_build_h(2, 4), 4), (O.ldpc_build_h(1, 8), 8), (O.ldpc_build_h(2, 32), 32),
+                          (O.ldpc_build_h(2, 50), 32), ((rng.random((12, 30)) < 0.2).astype(np.int8), None)]:
+        lp, lanes = layers(H)
+        assert lp[0] == 0 and lp[-1] == H.shape[0] and np.all(np.diff(lp) > 0) and np.diff(lp).max() <= 32
+        for a, b in zip(lp[:-1], lp[1:]):
+            assert H[a:b].astype(np.int64).sum(axis=0).max() <= 1          # rows of a layer share no column
+            if b < H.shape[0] and b - a < 32:
+                assert (H[a:b].sum(axis=0) * H[b]).any()                   # greedy: the next row really clashes
+        if want_lanes is not None:
+            assert lanes == want_lanes
+        else:
+            assert lanes in (0, 4, 8, 16, 32) and (lanes == 0) == (np.diff(lp).max() < 4)
