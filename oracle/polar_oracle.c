@@ -225,6 +225,9 @@ int po_crc_check(const int8_t *msg_crc, int len, const char *poly) {
 
 typedef struct { const uint8_t *frozen; int8_t *u_hat; } sc_ctx;
 
+/* (gcc cannot see that half >= 1 fills tmp[0..half) before the recursive call reads it) */
+#pragma GCC diagnostic push
+#pragma GCC diagnostic ignored "-Wmaybe-uninitialized"
 static void sc_segment(sc_ctx *c, const double *seg, int size, int start, int8_t *bits_out) {
     if (size == 1) { /* :147-154 */
         int8_t bit = c->frozen[start] ? 0 : (int8_t)(seg[0] < 0);
@@ -241,6 +244,7 @@ static void sc_segment(sc_ctx *c, const double *seg, int size, int start, int8_t
     sc_segment(c, tmp, half, start + half, rb);
     for (int i = 0; i < half; i++) { bits_out[i] = lb[i] ^ rb[i]; bits_out[half + i] = rb[i]; } /* :163 */
 }
+#pragma GCC diagnostic pop
 
 int po_sc_decode(const double *llr, int N, const int32_t *info_set, int K, int8_t *out_bits) {
     if (ilog2_exact(N) < 0 || N > PO_MAXN) return PO_EINVAL;
