@@ -150,10 +150,10 @@ typedef struct {
     int64_t n_frames;
 } pb200_sweep_cfg;
 /* d_beta: NULL or f32[K,K]; d_counters: int64[PB200_NCOUNTERS] on the device;
- * d_frame_bit_errors: NULL or u8[n_frames] per-frame bit errors of the LAST decoder run (for the
- * adaptive stop of run_ber_sweep.py:127), d_frame_work: NULL or u8[n_frames] attempts-1. */
+ * d_frame_bit_errors: NULL or u16[n_frames] per-frame bit errors of the LAST decoder run (for the
+ * adaptive stop of run_ber_sweep.py:127; exact: K <= 512 < 65536), d_frame_work: NULL or u16[n_frames] attempts-1. */
 int pb200_sweep(pb200_engine *e, const pb200_sweep_cfg *cfg, const float *d_beta, int64_t *d_counters,
-                uint8_t *d_frame_bit_errors, uint8_t *d_frame_work, void *stream);
+                uint16_t *d_frame_bit_errors, uint16_t *d_frame_work, void *stream);
 
 /* Generate the channel only (payload -> CRC -> encode -> [NR] -> BPSK + AWGN -> LLR), same Philox
  * stream as pb200_sweep: msg[B,K] u8 (NULL ok), llr[B,E or N] f32. */
@@ -220,8 +220,8 @@ typedef struct {
     int64_t frame_begin;
     int64_t n_frames;
 } pb200_ldpc_sweep_cfg;
-int pb200_ldpc_sweep(pb200_ldpc *e, const pb200_ldpc_sweep_cfg *cfg, int64_t *d_counters, uint8_t *d_frame_bit_errors,
-                     uint8_t *d_frame_work, void *stream);
+int pb200_ldpc_sweep(pb200_ldpc *e, const pb200_ldpc_sweep_cfg *cfg, int64_t *d_counters, uint16_t *d_frame_bit_errors,
+                     uint16_t *d_frame_work, void *stream);
 /* channel only, same Philox stream: payload[B,k_payload] u8 (NULL ok), llr[B,E] f64 */
 int pb200_ldpc_channel_batch(pb200_ldpc *e, const pb200_ldpc_sweep_cfg *cfg, uint8_t *d_payload, double *d_llr,
                              void *stream);

@@ -434,7 +434,7 @@ static int get_crc_tab(pb200_ldpc* e, int kp, unsigned long long poly, int deg, 
     return PB200_OK;
 }
 
-static int sweep_common(pb200_ldpc* e, const pb200_ldpc_sweep_cfg* c, int64_t* d_counters, uint8_t* d_fbe, uint8_t* d_fwork,
+static int sweep_common(pb200_ldpc* e, const pb200_ldpc_sweep_cfg* c, int64_t* d_counters, uint16_t* d_fbe, uint16_t* d_fwork,
                         uint8_t* d_payload, double* d_llr, bool chan_only, void* stream) {
     if (!e || !c) return lfail(PB200_EINVAL, "engine / cfg is NULL");
     const int k = e->n - e->m;
@@ -443,7 +443,7 @@ static int sweep_common(pb200_ldpc* e, const pb200_ldpc_sweep_cfg* c, int64_t* d
     if (c->E <= 0) return lfail(PB200_EINVAL, "E must be positive");
     if (!(c->noise_var > 0.0)) return lfail(PB200_EINVAL, "noise_var must be positive");
     if (c->n_frames < 0) return lfail(PB200_EINVAL, "n_frames must be >= 0");
-    if (c->max_iter > 255) return lfail(PB200_ENOSUP, "max_iter > 255 is not supported by the per-frame work counters");
+    if (c->max_iter > 65535) return lfail(PB200_ENOSUP, "max_iter > 65535 is not supported by the per-frame work counters");
     unsigned long long poly = 0;
     int deg = 0;
     if (c->k_crc > 0) {
@@ -512,7 +512,7 @@ static int sweep_common(pb200_ldpc* e, const pb200_ldpc_sweep_cfg* c, int64_t* d
 }
 
 extern "C" int pb200_ldpc_sweep(pb200_ldpc* e, const pb200_ldpc_sweep_cfg* cfg, int64_t* d_counters,
-                                uint8_t* d_frame_bit_errors, uint8_t* d_frame_work, void* stream) {
+                                uint16_t* d_frame_bit_errors, uint16_t* d_frame_work, void* stream) {
     return sweep_common(e, cfg, d_counters, d_frame_bit_errors, d_frame_work, nullptr, nullptr, false, stream);
 }
 

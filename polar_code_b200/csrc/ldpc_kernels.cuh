@@ -192,8 +192,8 @@ struct LdpcSweepArgs {
     int max_iter, early_stop;
     double alpha;
     unsigned long long* counters;   // [16] : [0] frames [1] frame errors [2] bit errors [7] iterations (work)
-    uint8_t* frame_bit_errors;      // [n_frames] or null
-    uint8_t* frame_work;            // [n_frames] or null
+    uint16_t* frame_bit_errors;     // [n_frames] or null (exact: k <= n <= 4096)
+    uint16_t* frame_work;           // [n_frames] or null
     uint8_t* payload_out;           // channel-only mode: [n_frames][kp] or null
     double* llr_out;                // channel-only mode: [n_frames][E]; non-null = do not decode
     double* gscratch;
@@ -293,8 +293,8 @@ __global__ void ldpc_sweep_kernel(LdpcCode c, LdpcGen g, LdpcSweepArgs a) {
         uint32_t be = 0;
         for (int j = 0; j < a.kp; ++j) be += (uint32_t)(st[j * T] < 0.0) ^ ((msg[(j >> 5) * T] >> (j & 31)) & 1u);
         n_frames += 1; n_fe += be > 0; n_be += be; n_work += (unsigned)used;
-        if (a.frame_bit_errors) a.frame_bit_errors[fi] = (uint8_t)(be > 255 ? 255 : be);
-        if (a.frame_work) a.frame_work[fi] = (uint8_t)(used > 255 ? 255 : used);
+        if (a.frame_bit_errors) a.frame_bit_errors[fi] = (uint16_t)be;
+        if (a.frame_work) a.frame_work[fi] = (uint16_t)(used > 65535 ? 65535 : used);
     }
     if (a.llr_out) return;
     // warp-level reduction, one atomic per warp and counter
@@ -580,8 +580,8 @@ __global__ void ldpc_sweep_group_kernel(LdpcCode c, LdpcGen g, LdpcLayers L, Ldp
         for (int o = 1; o < G; o <<= 1) be += __shfl_xor_sync(0xffffffffu, be, o);
         if (valid && li == 0) {
             n_frames += 1; n_fe += be > 0; n_be += be; n_work += (unsigned)used;
-            if (a.frame_bit_errors) a.frame_bit_errors[fi] = (uint8_t)(be > 255 ? 255 : be);
-            if (a.frame_work) a.frame_work[fi] = (uint8_t)(used > 255 ? 255 : used);
+            if (a.frame_bit_errors) a.frame_bit_errors[fi] = (uint16_t)be;
+            if (a.frame_work) a.frame_work[fi] = (uint16_t)(used > 65535 ? 65535 : used);
         }
         __syncwarp();
     }

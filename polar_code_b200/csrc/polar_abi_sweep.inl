@@ -210,7 +210,7 @@ static void span_mask(const pb200_engine* e, int span, uint32_t* mask) {
 }
 
 extern "C" int pb200_sweep(pb200_engine* e, const pb200_sweep_cfg* c, const float* d_beta, int64_t* d_counters,
-                           uint8_t* d_frame_bit_errors, uint8_t* d_frame_work, void* stream) {
+                           uint16_t* d_frame_bit_errors, uint16_t* d_frame_work, void* stream) {
     int rc = check_sweep_cfg(e, c);
     if (rc) return rc;
     if (!d_counters) return fail(PB200_EINVAL, "counters is NULL");

@@ -100,8 +100,12 @@ __device__ __forceinline__ float softplus_tail(float L) {
 #ifndef PB_DEFAULT_HS
 #define PB_DEFAULT_HS 5
 #endif
-// staged channel rows: [frame][chan_stride(N)] floats -- rows stay 16-byte aligned for vector loads
-__host__ __device__ inline int chan_stride(int N) { return N + 4; }
+// Channel LLRs of a warp's FPW frames are ALWAYS staged in the warp's global scratch, frame-interleaved:
+// element i of frame f at chan[i * FPW + f].  The MP lanes of a group read the same word and the FPW groups read FPW
+// consecutive words, so a warp-wide channel load is one 32-byte sector (one L1 wavefront) instead of one line per
+// frame -- reading the caller's rows in place cost a third of all L1 wavefronts of the list kernels, which is what
+// bounds them (l1tex data-pipe wavefronts 85 % of peak, profiles/r01_v9_*).
+__host__ __device__ inline int chan_stride(int N) { return N + 4; }       // floats reserved per frame (sizing only)
 
 template <int MP> struct DefaultHS { static constexpr int value = PB_DEFAULT_HS; };
 
@@ -116,13 +120,15 @@ __host__ __device__ inline int tree_rows_global(int N, int hs) {
     return all > cap ? all - cap : 0;
 }
 
-constexpr int kXchgBytes = 32 * 16 + 32 * 2 * 4;   // candidate keys + rank-sorted high words
+// exchange area of a warp: candidate keys [2][32][2] u64 (one buffer for even, one for odd phases) + the rank table of
+// the prune: one word per rank and group, (2*MP + 1) * (32/MP) <= 80 words (see ListDecoder::run)
+constexpr int kXchgBytes = 2 * 32 * 16 + 80 * 4;
 
 template <int MP, int HS = DefaultHS<MP>::value>
 struct WarpMem {
     float* ts;            // shared tree base:  element (h,i), h <  HS, at ts[((2^h-2)+i)*32 + lane]
     float* tg;            // global tree base (pre-offset): element (h,i), h >= HS, at tg[((2^h-2)+i)*32 + lane]
-    float* chan;          // [FPW][chan_stride(N)] staged channel LLRs (global scratch); unused when rows are read in place
+    float* chan;          // [N][FPW] staged channel LLRs, frame-interleaved (global scratch)
     float* scr;           // >= 3*max(N/32,1) lane-interleaved rows of scratch for the encoder / bit stash
     unsigned long long* xchg;  // [32][2] candidate keys for the rank exchange / small per-frame scratch (shared)
     float* absl;          // [FPW][xk+1] DL-SCL only: |L0| of the reference path (flip.py:102) (shared)
@@ -141,7 +147,13 @@ struct WarpMem {
     // The |L0| rows of the DL-SCL retry kernel are only live BETWEEN two list decodes (trace walk -> beta scoring), when
     // the tree rows are dead: they alias the shared tree area behind the stash rows whenever they fit there.
     __host__ __device__ static size_t absl_bytes(int xk) { return xk ? (((size_t)FPW * (xk + 1) * 4 + 15) & ~(size_t)15) : 0; }
-    __host__ __device__ static size_t stash_bytes(int N) { return (size_t)3 * (N >= 32 ? N / 32 : 1) * 32 * 4; }
+    // (the head of the tree area doubles as the bit stash of the output stage and as the coalescing tile of
+    //  stage_channel_rows, both of which may run while the |L0| rows are live)
+    static constexpr size_t kTileBytes = (size_t)FPW * (32 + MP) * 4;
+    __host__ __device__ static size_t stash_bytes(int N) {
+        const size_t st = (size_t)3 * (N >= 32 ? N / 32 : 1) * 32 * 4;
+        return st > kTileBytes ? st : kTileBytes;
+    }
     __host__ __device__ static bool absl_aliases_tree(int N, int xk) {
         return xk && kTreeBytes >= stash_bytes(N) + absl_bytes(xk);
     }
@@ -179,6 +191,34 @@ struct WarpMem {
         scr = (kTreeRows >= need) ? ts : g;
     }
 };
+
+// Stage the channel rows of the warp's FPW frames into wm.chan (frame-interleaved, see chan_stride above).
+// row_of(f) -> pointer to the N floats of frame f of this warp, or nullptr (row of zeros); must be warp-uniform per f.
+// 32 columns at a time through a shared-memory tile [FPW][32 + MP] (the tree rows are dead before phase 0): rows are
+// read coalesced (one 128 B line per frame and chunk), the tile is read column-wise without bank conflicts
+// (bank = f * MP + column offset covers all 32 banks) and written out as full 128 B lines: 4 L1 wavefronts per 32
+// staged floats.
+template <int MP, typename WM, typename RowOf>
+__device__ __forceinline__ void stage_channel_rows(const WM& wm, int N, int lane, RowOf&& row_of) {
+    constexpr int FPW = 32 / MP, TS = 32 + MP;
+    static_assert((size_t)FPW * TS * 4 <= WM::kTreeBytes + kXchgBytes, "staging tile must fit the tree + exchange area");
+    float* tile = wm.ts;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        const int C = N - c0 < 32 ? N - c0 : 32;
+#pragma unroll
+        for (int f = 0; f < FPW; ++f) {
+            const float* r = row_of(f);
+            tile[f * TS + lane] = (r != nullptr && lane < C) ? r[c0 + lane] : 0.f;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < FPW; ++it) {
+            const int t = it * 32 + lane, f = t & (FPW - 1), di = t / FPW;
+            if (di < C) wm.chan[(c0 + di) * FPW + f] = tile[f * TS + di];
+        }
+        __syncwarp();
+    }
+}
 
 // ---------------------------------------------------------------------------
 // Bit-packed partial sums.  Height h holds 2^h bits:
@@ -325,8 +365,9 @@ struct Tree {
         else return g_op_packed(a, b, bw[2 + (K >= 4 ? 1 : 0)], g + G * (K & 3));     // H == 6: e < 32 iff K < 4
     }
 
-    // Produce height H (>= 1) from height H+1 held at src[i*STRIDE] (STRIDE 32: a tree slot, lane folded into src;
-    // STRIDE 1: the channel row) with OP 0 = f, 1 = g using the left bits of height H; store it in the own slot and
+    // Produce height H (>= 1) from height H+1 held at src[i*STRIDE] (a tree slot, STRIDE 32 with the lane folded into
+    // src, or the frame-interleaved channel rows, STRIDE FPW with the frame folded into src)
+    // with OP 0 = f, 1 = g using the left bits of height H; store it in the own slot and
     // continue with f down to the height-1 pair.
     //   H <= 3 : everything in registers.
     //   H 4..6 : depth-first in groups of 8 strided elements {g + G*k}: they reduce in registers to 4 values of
@@ -376,22 +417,7 @@ struct Tree {
                 if constexpr (H - 3 >= 2) o3[g * 32] = r;
                 else { if (g == 0) r0 = r; else r1 = r; }
             };
-            if constexpr (STRIDE == 1 && G >= 2 && MP == 1) {
-                // channel row (each lane walks its own row, i.e. every request touches up to 32 lines): read it with
-                // 8-byte loads, two neighbouring groups per iteration, to halve the L1 tag look-ups
-#pragma unroll 1
-                for (int g = 0; g < G; g += 2) {
-                    float x0[8], y0[8], x1[8], y1[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const float2 xa = *reinterpret_cast<const float2*>(src + g + G * k);
-                        const float2 ya = *reinterpret_cast<const float2*>(src + g + G * k + S);
-                        x0[k] = xa.x; x1[k] = xa.y; y0[k] = ya.x; y1[k] = ya.y;
-                    }
-                    group(g, x0, y0);
-                    group(g + 1, x1, y1);
-                }
-            } else {
+            {
 #pragma unroll 1
                 for (int g = 0; g < G; ++g) {
                     float x[8], y[8];

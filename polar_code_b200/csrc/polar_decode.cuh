@@ -25,7 +25,7 @@ struct ListDecoder {
         const int n = code.n;
         const int slot = lane & (MP - 1), gbase = lane & ~(MP - 1);
         if constexpr (C1) {
-            if (n == 2) TreeT::template produce<1, 1, 1>(chanf, p.bw, wm, lane, a, b);      // N = 4: straight from the channel row
+            if (n == 2) TreeT::template produce<1, 1, FPW>(chanf, p.bw, wm, lane, a, b);    // N = 4: straight from the channel row
             else {
                 const uint32_t q = (p.P >> 4) & 0xfu;                                         // slot holding height 2
                 TreeT::template produce<1, 1, 32>(wm.ts + 2 * 32 + gbase + q, p.bw, wm, lane, a, b);
@@ -33,20 +33,20 @@ struct ListDecoder {
             p.P = (p.P & ~0xfu) | (uint32_t)slot;
             return;
         }
-        if (n == 1) { a = chanf[0]; b = chanf[1]; return; }      // N = 2: the channel row is the pair
+        if (n == 1) { a = chanf[0]; b = chanf[FPW]; return; }    // N = 2: the channel row is the pair
         const int c = (phi == 0) ? n - 1 : __ffs(phi) - 1;       // first height produced (>= 1)
         if (c == n - 1) {
-            // height n-1 straight from the channel row (stride 1): f at phi = 0, g at phi = N/2
+            // height n-1 straight from the staged channel rows (stride FPW): f at phi = 0, g at phi = N/2
             if (phi == 0) {
                 switch (c) {
-#define PB_CASE(HH) case HH: if constexpr (HH < LOGMAX) TreeT::template produce<HH, 0, 1>(chanf, p.bw, wm, lane, a, b); break;
+#define PB_CASE(HH) case HH: if constexpr (HH < LOGMAX) TreeT::template produce<HH, 0, FPW>(chanf, p.bw, wm, lane, a, b); break;
                     PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7) PB_CASE(8)
 #undef PB_CASE
                     default: break;
                 }
             } else {
                 switch (c) {
-#define PB_CASE(HH) case HH: if constexpr (HH < LOGMAX) TreeT::template produce<HH, 1, 1>(chanf, p.bw, wm, lane, a, b); break;
+#define PB_CASE(HH) case HH: if constexpr (HH < LOGMAX) TreeT::template produce<HH, 1, FPW>(chanf, p.bw, wm, lane, a, b); break;
                     PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7) PB_CASE(8)
 #undef PB_CASE
                     default: break;
@@ -108,12 +108,19 @@ struct ListDecoder {
         for (int k = 0; k < BW; ++k) p.bw[k] = 0;
 #pragma unroll
         for (int k = 0; k < XW; ++k) p.xh[k] = 0;
-        p.m = 0.0;
         p.r = 0;
         p.alive = frame_valid && ((lane & (MP - 1)) == 0);   // scl.py:135 one initial path
+        // List kernels: a lane without a live path carries the DEAD metric 2^1000.  Adding softplus terms leaves it
+        // unchanged, its candidates sort behind every real one, and "alive" is just (metric < 2^992): no alive
+        // flags, no selects in the key construction.
+        p.m = (MP > 1 && !p.alive) ? kDeadMetric : 0.0;
     }
+    static constexpr double kDeadMetric = 1.0715086071862673e+301;      // 2^1000 = 0x7e70000000000000
+    static constexpr uint32_t kDeadHigh = 0x7e000000u;                   // high word of 2^992: alive <=> high word below
+    static __device__ __forceinline__ bool metric_alive(double m) { return (uint32_t)__double2hiint(m) < kDeadHigh; }
 
-    // Decode the FPW frames of this warp; `chanf` = this lane's frame's channel row (N floats, stride 1).
+    // Decode the FPW frames of this warp; `chanf` = wm.chan + (frame of this lane within the warp): the staged,
+    // frame-interleaved channel row (element i at chanf[i * FPW], see stage_channel_rows).
     // fmask/fval (FORCED): per-frame masks over phases -- bit phi of fmask set <=> u_phi is forced to bit phi of
     // fval (scl.py:138-144,155-161).
     // TRACE: also record, per information phase j, the leaf LLR every slot saw (wm.hist[j][lane]) and the slot each
@@ -126,7 +133,12 @@ struct ListDecoder {
         const int N = code.N;
         const uint32_t M = (uint32_t)code.M;
         const int slot = lane & (MP - 1), gbase = lane & ~(MP - 1);
-        uint32_t* hs = reinterpret_cast<uint32_t*>(wm.xchg + 64);   // [32][2] high key words by rank (near-tie test)
+        // rank table of the prune: entry (group g, rank r) at word r * GN + g (GN groups per warp), so that the reads of the
+        // entries slot / slot + 1 by all 32 lanes are conflict-free; a lane beyond the list size M reads the last rank,
+        // which is then always a dead candidate
+        constexpr int GN = 32 / MP;
+        uint32_t* tab = reinterpret_cast<uint32_t*>(wm.xchg + 128) + lane / MP;
+        const int ridx = ((uint32_t)slot < M ? slot : 2 * MP - 1) * GN;
         uint32_t tie = 0;
         uint32_t cur_info = 0, cur_fm = 0, cur_fv = 0;   // word phi/32 of the info / force masks
         float a = 0.f, b = 0.f;                          // height-1 pair of the current phase pair
@@ -170,13 +182,13 @@ struct ListDecoder {
             } else {
                 const float tail = softplus_tail(L);
                 const double dtail = (double)tail;
-                const double m0 = p.m + ((double)fmaxf(-L, 0.f) + dtail);          // bit 0: logaddexp(0,-L)
-                bool a0 = p.alive, a1 = p.alive && is_info;
-                if (is_forced) {
-                    a0 = a0 && (forced_val == 0);
-                    a1 = a1 && (forced_val == 1);
-                }
+                double m0 = p.m + ((double)fmaxf(-L, 0.f) + dtail);                // bit 0: logaddexp(0,-L)
                 if constexpr (MP == 1) {
+                    bool a0 = p.alive, a1 = p.alive && is_info;
+                    if (is_forced) {
+                        a0 = a0 && (forced_val == 0);
+                        a1 = a1 && (forced_val == 1);
+                    }
                     if constexpr (TRACE) { if (is_info) { wm.hist[jinfo * 32 + lane] = L; ++jinfo; } }
                     const double m1 = p.m + ((double)fmaxf(L, 0.f) + dtail);       // bit 1: logaddexp(0, L)
                     bool pick1 = a1 && (!a0 || m1 < m0);
@@ -195,63 +207,65 @@ struct ListDecoder {
                         bit = 0;
                     } else {
                         // Keys: IEEE bits of the (non-negative) fp64 metric with the stable-sort tie-break 2*rank+bit in
-                        // the 4 lowest mantissa bits.  They order identically as integers and as doubles, so the rank
-                        // compares run on the otherwise idle FP64 pipe (one DSETP each).  A dead candidate gets a huge
-                        // finite key that is unique in its group, so EVERY candidate has a unique rank (dead ones last).
-                        const double m1 = p.m + ((double)fmaxf(L, 0.f) + dtail);   // bit 1: logaddexp(0, L)
-                        const unsigned long long dead = 0x7fe0000000000000ull | (unsigned long long)(2 * slot);
-                        const unsigned long long k0 = a0 ? (((unsigned long long)__double_as_longlong(m0) & ~15ull) | (2u * p.r)) : dead;
-                        const unsigned long long k1 = a1 ? (((unsigned long long)__double_as_longlong(m1) & ~15ull) | (2u * p.r + 1u)) : (dead | 1ull);
-                        reinterpret_cast<ulonglong2*>(wm.xchg)[lane] = make_ulonglong2(k0, k1);
+                        // the 4 lowest mantissa bits (the path in slot s IS the path of rank s, see below).  They order
+                        // identically as integers and as doubles, so the rank compares run on the otherwise idle FP64
+                        // pipe (one DSETP each).  Dead lanes carry the dead metric, so every candidate has a unique
+                        // rank (dead ones last, in slot order).
+                        double m1 = p.m + ((double)fmaxf(L, 0.f) + dtail);         // bit 1: logaddexp(0, L)
+                        if constexpr (FORCED) {                                    // scl.py:155-161: a forced bit kills the other child
+                            if (is_forced) { if (forced_val) m0 = kDeadMetric; else m1 = kDeadMetric; }
+                        }
+                        const uint32_t h0 = (uint32_t)__double2hiint(m0), h1 = (uint32_t)__double2hiint(m1);
+                        const uint32_t l0 = ((uint32_t)__double2loint(m0) & ~15u) | (2u * slot);
+                        const uint32_t l1 = ((uint32_t)__double2loint(m1) & ~15u) | (2u * slot + 1u);
+                        // the keys of even and odd phases live in two buffers: a lane may already publish the keys of
+                        // the next phase while another one still fetches its new metric from this phase's keys
+                        uint4* keys = reinterpret_cast<uint4*>(wm.xchg + (odd ? 64 : 0));
+                        keys[lane] = make_uint4(l0, h0, l1, h1);
                         __syncwarp();
-                        const double d0 = __longlong_as_double((long long)k0), d1 = __longlong_as_double((long long)k1);
+                        const double d0 = __hiloint2double((int)h0, (int)l0), d1 = __hiloint2double((int)h1, (int)l1);
                         uint32_t rank0 = 0, rank1 = 0;
 #pragma unroll
                         for (int j = 0; j < MP; ++j) {
-                            const ulonglong2 o = reinterpret_cast<const ulonglong2*>(wm.xchg)[gbase + j];
-                            const double ox = __longlong_as_double((long long)o.x), oy = __longlong_as_double((long long)o.y);
+                            const uint4 o = keys[gbase + j];
+                            const double ox = __hiloint2double((int)o.y, (int)o.x), oy = __hiloint2double((int)o.w, (int)o.z);
                             inc_if_lt(rank0, ox, d0); inc_if_lt(rank0, oy, d0);
                             inc_if_lt(rank1, ox, d1); inc_if_lt(rank1, oy, d1);
                         }
-                        const bool s0 = a0 && rank0 < M, s1 = a1 && rank1 < M;   // scl.py:174 keep the M best
-                        // near-tie test on rank-sorted neighbours: a kept candidate and its successor within ~1e-6 relative
-                        const uint32_t h0 = (uint32_t)(k0 >> 32), h1 = (uint32_t)(k1 >> 32);
-                        hs[2 * gbase + rank0] = h0;                               // all 2*MP ranks of the group are written
-                        hs[2 * gbase + rank1] = h1;
+                        // scl.py:173-174: the sorted list, truncated to M.  Every candidate publishes itself under its
+                        // rank -- one word: high key word (for the near-tie test) and candidate id 2*slot+bit -- and
+                        // lane s then BECOMES the candidate of rank s: it reads entry s and pulls that candidate's
+                        // state from its parent lane.  Survivors therefore always sit in rank order (slot = rank): no
+                        // rank register, no survive/clone bookkeeping, and the neighbour s+1 of the near-tie test is a
+                        // fixed address.
+                        tab[rank0 * GN] = h0 * 16u + 2u * slot;
+                        tab[rank1 * GN] = h1 * 16u + (2u * slot + 1u);
                         __syncwarp();
-                        if (s0 && rank0 + 1 < 2 * MP && (uint32_t)(hs[2 * gbase + rank0 + 1] - h0) <= 2u) tie = 1;
-                        if (s1 && rank1 + 1 < 2 * MP && (uint32_t)(hs[2 * gbase + rank1 + 1] - h1) <= 2u) tie = 1;
-                        const bool dbl = s0 && s1, fre = !s0 && !s1;
-                        const uint32_t dm = (__ballot_sync(kFull, dbl) >> gbase) & GM;
-                        const uint32_t fm = (__ballot_sync(kFull, fre) >> gbase) & GM;
-                        int src = lane;
-                        bool take = false;
-                        if (fre) {
-                            const int k = __popc(fm & ((1u << slot) - 1u));
-                            uint32_t d = dm;
-#pragma unroll
-                            for (int i = 0; i < MP / 2; ++i) if (i < k) d &= d - 1;
-                            if (d) { src = gbase + __ffs(d) - 1; take = true; }
-                        }
+                        const uint32_t w = tab[ridx], wn = tab[ridx + GN];
+                        const int e = (int)(w & 15u);                 // candidate id: 2 * (slot of the parent) + bit
+                        const int src = gbase + (e >> 1);
                         if constexpr (TRACE) {
                             wm.hist[jinfo * 32 + lane] = L;
                             {   // lineage of all 32 lanes as bit planes: three ballots, one 16-byte store
-                                const uint32_t sl = (uint32_t)(src - gbase);
-                                const uint32_t b0 = __ballot_sync(kFull, sl & 1u), b1 = __ballot_sync(kFull, sl & 2u);
-                                const uint32_t b2 = MP > 4 ? __ballot_sync(kFull, sl & 4u) : 0u;
+                                const uint32_t b0 = __ballot_sync(kFull, e & 2), b1 = __ballot_sync(kFull, e & 4);
+                                const uint32_t b2 = MP > 4 ? __ballot_sync(kFull, e & 8) : 0u;
                                 if (lane == 0) *reinterpret_cast<uint4*>(wm.lin + jinfo * 4) = make_uint4(b0, b1, b2, 0u);
                             }
                             ++jinfo;
                         }
-                        // The second child of a doubly-surviving path moves into a freed slot.  Every lane reads from
-                        // `src`; lanes that take no clone have src == lane, so what they read back is their own state
-                        // and the assignments below need no select.
-                        // (a left buffer of height h is live only while bit h of phi is set: words of dead heights
-                        //  are rewritten before their next use and need not travel)
+                        // metric of the candidate = its key without the tie-break bits
+                        const uint2 kk = reinterpret_cast<const uint2*>(keys)[2 * gbase + e];
+                        p.m = __hiloint2double((int)kk.y, (int)(kk.x & ~15u));
+                        // near-tie: a kept (alive) candidate and its successor within ~1e-6 relative (high key words
+                        // <= 2 apart; the table holds them shifted by 4, i.e. modulo 2^28 -- far beyond any metric ratio)
+                        if (kk.y < kDeadHigh && (uint32_t)((wn | 15u) - w) <= 47u) tie = 1;
+                        // Every lane reads the path state from `src` (possibly itself).  For N <= 128 all four
+                        // partial-sum words travel unconditionally (a branch around a shuffle costs more than the
+                        // shuffle); the wide buffers of N = 256 / 512 travel only while they are live (a left buffer
+                        // of height h is live while bit h of phi is set).
                         p.P = __shfl_sync(kFull, p.P, src);
-                        p.bw[0] = __shfl_sync(kFull, p.bw[0], src);
-                        if (phi & 32) p.bw[1] = __shfl_sync(kFull, p.bw[1], src);
-                        if (phi & 64) { p.bw[2] = __shfl_sync(kFull, p.bw[2], src); p.bw[3] = __shfl_sync(kFull, p.bw[3], src); }
+#pragma unroll
+                        for (int k = 0; k < (BW < 4 ? BW : 4); ++k) p.bw[k] = __shfl_sync(kFull, p.bw[k], src);
                         if constexpr (BW >= 8) {
                             if (phi & 128) {
 #pragma unroll
@@ -264,13 +278,8 @@ struct ListDecoder {
                                 for (int k = 8; k < 16; ++k) p.bw[k] = __shfl_sync(kFull, p.bw[k], src);
                             }
                         }
-                        const double m2 = __shfl_sync(kFull, m1, src);        // child 1 of src
-                        const uint32_t r2 = __shfl_sync(kFull, rank1, src);
                         if (!odd) { a = __shfl_sync(kFull, a, src); b = __shfl_sync(kFull, b, src); }
-                        p.m = s0 ? m0 : m2;                                   // keep child 0 if it survives, else child 1 (own or cloned)
-                        p.r = s0 ? rank0 : r2;
-                        bit = s0 ? 0u : 1u;
-                        p.alive = s0 || s1 || take;
+                        bit = (uint32_t)(e & 1);
                     }
                 }
             }
@@ -279,7 +288,6 @@ struct ListDecoder {
                 if (half) set_bit_odd<false>(code, p, phi, bit);
                 else set_bit_odd<true>(code, p, phi, bit);
             } else set_bit_odd<R == 1>(code, p, phi, bit);
-            if constexpr (MP > 1) __syncwarp();
         };
         if constexpr (!FORCED && !TRACE && MP == 1) {
             // thread-per-frame kernels (no rank/clone code): fully static blocks of four phases (measured +7 % over pairs)
@@ -308,7 +316,8 @@ struct ListDecoder {
         }
         // final list order = metric order (scl.py:173-174,183-188), ties by the last computed rank
         if constexpr (MP > 1 && METRIC) {
-            const unsigned long long kf = p.alive ? (((unsigned long long)__double_as_longlong(p.m) & ~15ull) | p.r) : ~0ull;
+            p.alive = metric_alive(p.m);
+            const unsigned long long kf = p.alive ? (((unsigned long long)__double_as_longlong(p.m) & ~15ull) | (uint32_t)slot) : ~0ull;
             wm.xchg[lane] = kf;
             __syncwarp();
             uint32_t rank = 0, cnt = 0;

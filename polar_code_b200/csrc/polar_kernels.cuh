@@ -32,15 +32,15 @@ struct DecodeArgs {
 };
 
 // NR rate matching: stage the de-rate-matched + de-interleaved row of each of the warp's FPW frames in wm.chan
-// ([f][chan_stride(N)], global scratch).  rate_match.py:19-39: mean of the repeats, -1.0 where nothing was sent;
-// interleaver.py:26-37: gather through rm_src.  (Plain rows are read in place from the caller's buffer.)
+// (frame-interleaved like every staged channel row).  rate_match.py:19-39: mean of the repeats, -1.0 where nothing was
+// sent; interleaver.py:26-37: gather through rm_src.
 template <int MP, typename WM>
 __device__ __forceinline__ void load_channel(const Code& code, const Tables& tb, const WM& wm, const float* llr,
                                              int in_len, int64_t frame0, int64_t B, int lane) {
     constexpr int FPW = 32 / MP;
-    const int N = code.N, n = code.n;
+    const int N = code.N;
     for (int e = lane; e < FPW * N; e += 32) {
-        const int f = e >> n, i = e & (N - 1);
+        const int f = e & (FPW - 1), i = e / FPW;          // e = i * FPW + f: the stores are coalesced
         const int64_t frame = frame0 + f;
         float v = 0.f;
         if (frame < B) {
@@ -52,7 +52,7 @@ __device__ __forceinline__ void load_channel(const Code& code, const Tables& tb,
                 v = cnt ? acc / (float)cnt : -1.0f;
             }
         }
-        wm.chan[f * chan_stride(N) + i] = v;
+        wm.chan[e] = v;
     }
     __syncwarp();
 }
@@ -137,12 +137,11 @@ __global__ void __launch_bounds__(LOGMAX <= 7 ? 1024 : 512) decode_kernel(const 
         const int64_t frame0 = g * FPW;
         const int64_t frame = frame0 + lane / MP;
         const bool valid = frame < a.B;
-        const float* chanf;
-        if (tb.E == 0) chanf = a.llr + (valid ? frame : 0) * (int64_t)a.in_len;      // rows are decoded in place
-        else {
-            load_channel<MP, WM>(code, tb, wm, a.llr, a.in_len, frame0, a.B, lane);
-            chanf = wm.chan + (lane / MP) * chan_stride(code.N);
-        }
+        if (tb.E == 0) {
+            stage_channel_rows<MP>(wm, code.N, lane, [&](int f) -> const float* {
+                return frame0 + f < a.B ? a.llr + (frame0 + f) * (int64_t)a.in_len : nullptr; });
+        } else load_channel<MP, WM>(code, tb, wm, a.llr, a.in_len, frame0, a.B, lane);
+        const float* chanf = wm.chan + lane / MP;
         uint32_t flags = 0;
         uint32_t fmask[XW], fval[XW];
         if constexpr (FORCED) load_force<XW>(code, a.force, frame, valid, fmask, fval, flags);

@@ -74,8 +74,8 @@ struct SweepArgs {
     uint32_t be_mask[kMaxWords];   // phases whose bits are compared for bit errors
     const float* beta;
     unsigned long long* counters;
-    uint8_t* frame_bit_errors;
-    uint8_t* frame_work;
+    uint16_t* frame_bit_errors;   // exact per-frame counts (K <= 512, retries <= 65535)
+    uint16_t* frame_work;
     // DL API outputs (indexed by frame - frame_begin)
     uint8_t* best_bits;
     uint32_t* best_words;
@@ -231,9 +231,8 @@ __device__ __forceinline__ void gen_channel(const Code& code, const Tables& tb, 
     const int Eeff = nr ? tb.E : N;
     const int nblk = N >= 4 ? N / 4 : 1;
     const int rounds = (Eeff + N - 1) / N;
-    const int lg_nblk = code.n >= 2 ? code.n - 2 : 0;            // nblk = 2^lg_nblk
     for (int item = lane; item < FPW * nblk; item += 32) {
-        const int f = item >> lg_nblk, jb = item & (nblk - 1);
+        const int f = item & (FPW - 1), jb = item / FPW;             // frame fastest: the interleaved stores are full sectors
         const long long fr = fids[f];
         if (fr < 0) continue;
         if (!nr && N >= 4) {
@@ -247,7 +246,10 @@ __device__ __forceinline__ void gen_channel(const Code& code, const Tables& tb, 
             v.z = fmaf(cc.sigma, z[2], 1.0f - 2.0f * (float)((nib >> 2) & 1u)) * cc.scale;
             v.w = fmaf(cc.sigma, z[3], 1.0f - 2.0f * (float)((nib >> 3) & 1u)) * cc.scale;
             if (raw_out) *reinterpret_cast<float4*>(raw_out + (fr - raw_base) * (long long)N + jb * 4) = v;
-            else *reinterpret_cast<float4*>(wm.chan + f * chan_stride(N) + jb * 4) = v;
+            else {
+                float* d = wm.chan + (jb * 4) * FPW + f;                 // frame-interleaved staging (stage_channel_rows)
+                d[0] = v.x; d[FPW] = v.y; d[2 * FPW] = v.z; d[3 * FPW] = v.w;
+            }
             continue;
         }
         // general path (NR rate matching, N = 2): this lane owns the positions p = 4 jb + c of EVERY repetition round,
@@ -279,7 +281,7 @@ __device__ __forceinline__ void gen_channel(const Code& code, const Tables& tb, 
                     const int dst = nr ? (int)__ldg(&cc.rm_dst[p]) : p;
                     if (dst >= 0) {
                         const int cnt = nr ? (int)__ldg(&tb.rm_cnt[dst]) : 1;
-                        wm.chan[f * chan_stride(N) + dst] = cnt == 0 ? -1.0f : (cnt == 1 ? acc[c] : acc[c] / (float)cnt);
+                        wm.chan[dst * FPW + f] = cnt == 0 ? -1.0f : (cnt == 1 ? acc[c] : acc[c] / (float)cnt);
                     }
                 }
             }
@@ -289,41 +291,43 @@ __device__ __forceinline__ void gen_channel(const Code& code, const Tables& tb, 
     if (nr && !raw_out && cc.has_pads) {
         // internal positions fed by an interleaver pad carry 0.0 (interleaver.py:33-34)
         for (int e = lane; e < FPW * N; e += 32) {
-            const int f = e >> code.n, i = e & (N - 1);
-            if (fids[f] >= 0 && __ldg(&tb.rm_cnt[i]) < 0) wm.chan[f * chan_stride(N) + i] = 0.f;
+            const int f = e & (FPW - 1), i = e / FPW;
+            if (fids[f] >= 0 && __ldg(&tb.rm_cnt[i]) < 0) wm.chan[e] = 0.f;
         }
         __syncwarp();
     }
 }
 
 
-// Gather-load of channel LLRs for arbitrary frame ids (LLR-in mode of the DL-SCL retry kernel).
+__device__ __forceinline__ const float* shfl_ptr(const float* p, int src) {
+    return reinterpret_cast<const float*>(__shfl_sync(kFull, (unsigned long long)reinterpret_cast<uintptr_t>(p), src));
+}
+
+// Stage the channel LLRs of arbitrary frames (LLR-in mode): `row` = this lane's frame's row in the caller's buffer
+// (nullptr = none).  Plain rows go through the coalescing tile; with NR rate matching the de-rate-matched row is
+// gathered (rate_match.py:19-39, interleaver.py:26-37) straight into the frame-interleaved layout.
 template <int MP, typename WM>
-__device__ __forceinline__ void load_channel_ids(const Code& code, const Tables& tb, const WM& wm, const float* llr,
-                                                 int in_len, long long my_frame, long long frame_begin, int lane) {
+__device__ __forceinline__ void load_channel_ids(const Code& code, const Tables& tb, const WM& wm, const float* row, int lane) {
     constexpr int FPW = 32 / MP;
     const int N = code.N;
-    long long* fids = reinterpret_cast<long long*>(wm.xchg + 16);
-    if ((lane & (MP - 1)) == 0) fids[lane / MP] = my_frame;
-    __syncwarp();
+    if (tb.E == 0) {
+        stage_channel_rows<MP>(wm, N, lane, [&](int f) { return shfl_ptr(row, f * MP); });
+        return;
+    }
     for (int e = lane; e < FPW * N; e += 32) {
-        const int f = e >> code.n, i = e & (N - 1);
-        const long long fr = fids[f];
+        const int f = e & (FPW - 1), i = e / FPW;
+        const float* r = shfl_ptr(row, f * MP);              // (every lane runs the same number of iterations)
         float v = 0.f;
-        if (fr >= 0) {
-            const float* row = llr + (fr - frame_begin) * (long long)in_len;
-            if (tb.E == 0) v = row[i];
-            else {
-                const int p = tb.rm_src[i];
-                if (p >= 0) {
-                    float acc = 0.f;
-                    int cnt = 0;
-                    for (int q = p; q < tb.E; q += N) { acc += row[q]; ++cnt; }
-                    v = cnt ? acc / (float)cnt : -1.0f;
-                }
+        if (r != nullptr) {
+            const int p = tb.rm_src[i];
+            if (p >= 0) {
+                float acc = 0.f;
+                int cnt = 0;
+                for (int q = p; q < tb.E; q += N) { acc += r[q]; ++cnt; }
+                v = cnt ? acc / (float)cnt : -1.0f;
             }
         }
-        wm.chan[f * chan_stride(N) + i] = v;
+        wm.chan[e] = v;
     }
     __syncwarp();
 }
@@ -387,8 +391,8 @@ struct Sweep {
             acc[cDlFe] += (a.fe_mode == 0) ? (b.pass ? 0u : 1u) : (be ? 1u : 0u);
             acc[cDlUndet] += (b.pass && wrong) ? 1u : 0u;
             acc[cDlWork] += n_tried;
-            if (a.frame_bit_errors) a.frame_bit_errors[idx] = (uint8_t)min(be, 255u);
-            if (a.frame_work) a.frame_work[idx] = (uint8_t)min(n_tried, 255u);
+            if (a.frame_bit_errors) a.frame_bit_errors[idx] = (uint16_t)be;
+            if (a.frame_work) a.frame_work[idx] = (uint16_t)min(n_tried, 65535u);
         }
         acc[cRankTie] += (b.flags & PB_FLAG_RANK_TIE) ? 1u : 0u;
         const int xwn = code.N >= 32 ? code.N / 32 : 1;
@@ -408,7 +412,8 @@ struct Sweep {
     }
 
     // Warp-aggregated append of the leaders with `need` to the output queue.  `store` < 0: first time this frame is
-    // queued -> its channel row (chanf, N floats) is copied to llr_store[slot] and slot becomes its store index.
+    // queued -> its staged channel row (chanf, element i at chanf[i * FPW]) is copied to llr_store[slot] and slot
+    // becomes its store index.
     // Returns the queue slot of this lane's entry (-1: none).
     static __device__ __forceinline__ long long enqueue(const Code& code, const SweepArgs& a, int lane, bool need, long long frame, const Best& b,
                                                         const uint32_t (&tried)[XW], uint32_t n_tried, const uint32_t (&u_sent)[XW],
@@ -436,7 +441,7 @@ struct Sweep {
             const long long gslot = __shfl_sync(kFull, (store < 0) ? slot : -1ll, lane & ~(MP - 1));
             if (gslot >= 0) {
                 float* dst = a.llr_store + gslot * (long long)code.N;
-                for (int i = lane & (MP - 1); i < code.N; i += MP) dst[i] = chanf[i];
+                for (int i = lane & (MP - 1); i < code.N; i += MP) dst[i] = chanf[i * FPW];
             }
         }
         return slot;
@@ -487,7 +492,7 @@ __global__ void __launch_bounds__(PB_SWEEP_THREADS) sweep_kernel(const Code code
         if (a.llr) {
 #pragma unroll
             for (int k = 0; k < XW; ++k) u_sent[k] = 0;
-            load_channel_ids<MP, WM>(code, tb, wm, a.llr, a.in_len, my_frame, a.frame_begin, lane);
+            load_channel_ids<MP, WM>(code, tb, wm, valid ? a.llr + idx * (long long)a.in_len : nullptr, lane);
         } else {
             gen_channel<MP, XW, WM>(code, tb, a.cc, wm, my_frame, lane, u_sent, unc, true);
         }
@@ -495,7 +500,7 @@ __global__ void __launch_bounds__(PB_SWEEP_THREADS) sweep_kernel(const Code code
         uint32_t fm[XW], fv[XW];
         PathT p;
         S::DecU::init(p, lane, valid);
-        const float* chanf = wm.chan + (lane / MP) * chan_stride(code.N);
+        const float* chanf = wm.chan + lane / MP;
         S::DecU::template run<TRACE>(code, tb.info_mask, wm, p, lane, chanf, fm, fv, flags);
         typename S::Best b;
         S::pick_best(code, tb, p, lane, flags, b);
@@ -516,7 +521,7 @@ __global__ void __launch_bounds__(PB_SWEEP_THREADS) sweep_kernel(const Code code
                 }
                 if (a.cc.include_uncoded) { acc[cUncBe] += unc; acc[cUncFe] += unc ? 1u : 0u; }
                 if (a.retries < 0) {
-                    if (a.frame_bit_errors) a.frame_bit_errors[idx] = (uint8_t)min(be, 255u);
+                    if (a.frame_bit_errors) a.frame_bit_errors[idx] = (uint16_t)be;
                     if (a.frame_work) a.frame_work[idx] = 0;
                 }
             }
@@ -587,40 +592,39 @@ __global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_retry_ker
 
     for (;;) {
         // ---- idle groups pull the next queue entry --------------------------------------------------------
-        {
-            const uint32_t want = __ballot_sync(kFull, leader && !active && !exhausted);
-            if (want) {
-                unsigned int base = 0;
-                if (lane == 0) base = atomicAdd(a.q_out_count, (unsigned int)__popc(want));     // q_out_count = "next entry" cursor
-                base = __shfl_sync(kFull, base, 0);
-                long long idx = -1;
-                if (leader && !active && !exhausted) idx = (long long)base + __popc(want & ((1u << lane) - 1u));
-                idx = __shfl_sync(kFull, idx, gbase);
-                if (idx >= 0) {
-                    if (idx < (long long)n_in) {
-                        const Entry* e = reinterpret_cast<const Entry*>(a.q_in) + idx;
-                        my_frame = e->h.frame; eflags = e->h.flags; n_tried = e->h.n_tried; store = e->store;
+        const uint32_t want = __ballot_sync(kFull, leader && !active && !exhausted);
+        if (want) {
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(a.q_out_count, (unsigned int)__popc(want));     // q_out_count = "next entry" cursor
+            base = __shfl_sync(kFull, base, 0);
+            long long idx = -1;
+            if (leader && !active && !exhausted) idx = (long long)base + __popc(want & ((1u << lane) - 1u));
+            idx = __shfl_sync(kFull, idx, gbase);
+            if (idx >= 0) {
+                if (idx < (long long)n_in) {
+                    const Entry* e = reinterpret_cast<const Entry*>(a.q_in) + idx;
+                    my_frame = e->h.frame; eflags = e->h.flags; n_tried = e->h.n_tried; store = e->store;
 #pragma unroll
-                        for (int k = 0; k < XW; ++k) { u_ref[k] = e->u[k]; tried[k] = e->tried[k]; u_sent[k] = e->u_sent[k]; }
-                        active = true;
-                        const float* src = a.abs_store + store * (long long)K;     // written by the baseline pass
-                        for (int j = slot; j < K; j += MP) ab[j] = src[j];
-                    } else exhausted = true;
-                }
-                __syncwarp();
+                    for (int k = 0; k < XW; ++k) { u_ref[k] = e->u[k]; tried[k] = e->tried[k]; u_sent[k] = e->u_sent[k]; }
+                    active = true;
+                    const float* src = a.abs_store + store * (long long)K;     // written by the baseline pass
+                    for (int j = slot; j < K; j += MP) ab[j] = src[j];
+                } else exhausted = true;
             }
+            __syncwarp();
         }
         if (!__any_sync(kFull, active)) break;
         const bool valid = active;
-        // channel row of this frame: the LLR store (sweep mode), the caller's buffer (API mode), or -- with NR rate
-        // matching in API mode -- the de-rate-matched row staged by load_channel_ids
-        const float* chanf;
-        if (a.llr == nullptr) chanf = a.llr_store + (valid ? store : 0) * (long long)code.N;
-        else if (tb.E == 0) chanf = a.llr + (valid ? (my_frame - a.frame_begin) : 0) * (long long)a.in_len;
-        else {
-            load_channel_ids<MP, WM>(code, tb, wm, a.llr, a.in_len, valid ? my_frame : -1, a.frame_begin, lane);
-            chanf = wm.chan + fme * chan_stride(code.N);
+        // Channel rows: the LLR store (sweep mode) or the caller's buffer (API mode; with NR rate matching the
+        // de-rate-matched row).  They are re-staged only when some group of the warp took a new frame -- the staged rows
+        // of the other groups are unchanged (the decode never writes wm.chan).
+        if (want) {
+            const float* row = nullptr;
+            if (valid) row = (a.llr == nullptr) ? a.llr_store + store * (long long)code.N
+                                                : a.llr + (my_frame - a.frame_begin) * (long long)a.in_len;
+            load_channel_ids<MP, WM>(code, tb, wm, row, lane);
         }
+        const float* chanf = wm.chan + fme;
         // rank_indices (flip.py:104-108): first untried index of argsort(|L0| @ beta) = argmin over untried
         double m1 = 1e300, m2 = 1e300;
         int a1 = 0x7fffffff;

@@ -118,8 +118,8 @@ def run(args: argparse.Namespace) -> List[Dict[str, float]]:
         return _sweep_rows(args, eng, params_label, -1, None)
     info_set = construct_info_set(N, K_total)
     if args.scheme == "polar_scl":
-        if args.E != N:
-            raise ValueError("polar_scl transmits the mother code: E must equal N")
+        # like the reference (run_ber_sweep.py:240-245): the N-bit mother code is sent; E only enters the noise variance
+        # (rate = K_payload / E) and the N_or_E / rate columns, for polar_scl and dl_scl alike
         eng, params_label = engine_for(N, info_set, args.crc_poly), f"M={args.M}"
     elif args.scheme == "dl_scl":
         beta = np.load(args.beta)

@@ -54,13 +54,27 @@ def label_failures(eng, llr: torch.Tensor, M: int, info: torch.Tensor):
     return fail, abs_l0, label
 
 
-def generate_samples(args: argparse.Namespace) -> None:
+def _geometry(args: argparse.Namespace):
+    """(N, K_total, crc_poly, crc_bits): the reference is fixed to config.DEFAULTS (make_dataset.py:25-29); the optional
+    --N / --K_total / --crc_poly flags (absent from a reference-style Namespace) let a beta be trained for any
+    geometry, e.g. the 88 x 88 one run_ber_sweep --scheme dl_scl --K_payload 64 --K_crc 24 needs."""
     cfg = config.get_config()
+    N = getattr(args, "N", None) or cfg.N
+    K = getattr(args, "K_total", None) or cfg.K
+    poly = getattr(args, "crc_poly", None) or cfg.crc_poly
+    crc_bits = int(poly, 16).bit_length() - 1
+    if not 0 < crc_bits < K <= N:
+        raise ValueError("need 0 < CRC degree < K_total <= N")
+    return int(N), int(K), poly, crc_bits
+
+
+def generate_samples(args: argparse.Namespace) -> None:
+    N, K, crc_poly, crc_bits = _geometry(args)
     seed_all(args.seed)
-    info_set = construct_info_set(cfg.N, cfg.K)
-    eng = engine_for(cfg.N, info_set, cfg.crc_poly)
-    nv = mc.fer_noise_var(args.snr_db, cfg.K, cfg.N)
-    info = torch.zeros(cfg.K, dtype=torch.uint8, device=eng.dev)                   # attach_crc(0...0) = 0...0 (:31-33)
+    info_set = construct_info_set(N, K)
+    eng = engine_for(N, info_set, crc_poly)
+    nv = mc.fer_noise_var(args.snr_db, K, N)
+    info = torch.zeros(K, dtype=torch.uint8, device=eng.dev)                       # attach_crc(0...0) = 0...0 (:31-33)
 
     rows: List[torch.Tensor] = []
     labels: List[torch.Tensor] = []
@@ -69,7 +83,7 @@ def generate_samples(args: argparse.Namespace) -> None:
     for begin in range(0, args.frames, chunk):
         n = min(chunk, args.frames - begin)
         msg, llr = eng.channel(noise_var=nv, n_frames=n, frame_begin=begin, seed=args.seed, stream_id=0,
-                               k_payload=cfg.K - cfg.crc_bits)
+                               k_payload=K - crc_bits)
         # the channel kernel draws a random payload; flipping the LLR signs by its codeword gives the all-zero
         # codeword's observation under the same noise (the BPSK/AWGN channel is symmetric)
         llr = llr * (1.0 - 2.0 * eng.encode(msg).to(torch.float32))
@@ -78,12 +92,14 @@ def generate_samples(args: argparse.Namespace) -> None:
         failures += int((~good).sum().item())
         rows.append(abs_l0[good])
         labels.append(label[good])
-    abs_array = torch.cat(rows).cpu().numpy().astype(np.float32) if rows else np.zeros((0, cfg.K), np.float32)
+    abs_array = torch.cat(rows).cpu().numpy().astype(np.float32) if rows else np.zeros((0, K), np.float32)
     label_array = torch.cat(labels).cpu().numpy().astype(np.int32) if labels else np.zeros(0, np.int32)
     if label_array.size == 0:
         raise RuntimeError("No samples collected; consider increasing frames or SNR")
-    meta = {"M": args.M, "EbN0_dB": args.snr_db, "seed": args.seed, "frames": args.frames, "crc_poly": cfg.crc_poly,
-            "crc_bits": cfg.crc_bits, "samples": int(label_array.size), "failures": int(failures)}
+    meta = {"M": args.M, "EbN0_dB": args.snr_db, "seed": args.seed, "frames": args.frames, "crc_poly": crc_poly,
+            "crc_bits": crc_bits, "samples": int(label_array.size), "failures": int(failures)}
+    if (N, K) != (config.DEFAULTS.N, config.DEFAULTS.K):      # the reference's schema is kept for its own geometry
+        meta.update({"N": N, "K_total": K})
     out_path = Path(args.out)
     out_dir = out_path.parent if out_path.parent != Path("") else Path(".")
     out_dir.mkdir(parents=True, exist_ok=True)
@@ -99,6 +115,9 @@ def build_argparser() -> argparse.ArgumentParser:
     parser.add_argument("--frames", type=int, default=100000, help="Number of frames to simulate")
     parser.add_argument("--seed", type=int, default=0, help="RNG seed")
     parser.add_argument("--out", type=str, required=True, help="Output prefix for dataset shards")
+    parser.add_argument("--N", type=int, default=None, help="Code length (default: config.N)")
+    parser.add_argument("--K_total", type=int, default=None, help="Information bits incl. CRC (default: config.K)")
+    parser.add_argument("--crc_poly", type=str, default=None, help="CRC polynomial, hex with leading 1 (default: config.crc_poly)")
     return parser
 
 

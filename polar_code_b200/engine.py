@@ -32,6 +32,15 @@ def _ptr(t: Optional[torch.Tensor]):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
+def _u16(t: Optional[torch.Tensor], name: str, n: int) -> Optional[torch.Tensor]:
+    """Per-frame counter buffers are u16[n_frames] on the device side (exact counts); torch buffers are int16/uint16."""
+    if t is None:
+        return None
+    if t.element_size() != 2 or t.numel() < n or not t.is_contiguous() or not t.is_cuda:
+        raise ValueError(f"{name} must be a contiguous 16-bit CUDA tensor with at least n_frames elements")
+    return t
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -198,8 +207,11 @@ class PolarEngine:
               noise_var_uncoded: float = 1.0, beta=None, frame_bit_errors: Optional[torch.Tensor] = None,
               frame_work: Optional[torch.Tensor] = None) -> None:
         """Fused channel + decode + counters (run_fer_sweep.py:60-121 / run_ber_sweep.py:112-181).
-        `counters` is an int64[16] CUDA tensor that is ADDED to."""
+        `counters` is an int64[16] CUDA tensor that is ADDED to; `frame_bit_errors` / `frame_work` are optional 16-bit
+        per-frame outputs (bit errors of the last decoder run, attempts-1) for the adaptive stop."""
         b = self._dev(beta, torch.float32) if beta is not None else None
+        frame_bit_errors = _u16(frame_bit_errors, "frame_bit_errors", int(n_frames))
+        frame_work = _u16(frame_work, "frame_work", int(n_frames))
         kp = self.K if k_payload is None else int(k_payload)
         cfg = self._cfg(M=int(M), retries=int(retries), run_scl=int(run_scl), k_payload=kp, E=int(self.E),
                         frame_error_mode=int(frame_error_mode),

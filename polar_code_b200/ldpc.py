@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .engine import _ptr, _stream, require_cuda
+from .engine import _ptr, _stream, _u16, require_cuda
 
 
 def build_h_matrix(bg: int, Z: int) -> np.ndarray:
@@ -155,6 +155,8 @@ class LdpcEngine:
               frame_work: Optional[torch.Tensor] = None, **_ignored) -> None:
         """Fused channel + NMS decode + counters (run_ber_sweep.py:112-181, scheme nr_ldpc); `counters` is ADDED to."""
         sw = self._sw
+        frame_bit_errors = _u16(frame_bit_errors, "frame_bit_errors", int(n_frames))
+        frame_work = _u16(frame_work, "frame_work", int(n_frames))
         kp = self.k - sw["k_crc"] if k_payload is None else int(k_payload)
         cfg = self._cfg(k_payload=kp, early_stop=1, noise_var=noise_var, seed=seed, stream_id=stream_id,
                         frame_begin=frame_begin, n_frames=n_frames, **sw)

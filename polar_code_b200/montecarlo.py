@@ -136,7 +136,7 @@ def adaptive_cut(state: CutState, local_err: torch.Tensor, local_work: torch.Ten
     tensors with gloo and on CUDA tensors with NCCL."""
     dev = local_err.device
     rank, ws = world()
-    err = local_err.to(torch.int64)
+    err = local_err.to(torch.int64) & 0xFFFF          # the kernels write u16 (torch buffers are int16)
     csum = torch.cumsum(err, 0)
     local_total = csum[-1:].clone() if err.numel() else torch.zeros(1, dtype=torch.int64, device=dev)
     if ws > 1:
@@ -167,7 +167,7 @@ def adaptive_cut(state: CutState, local_err: torch.Tensor, local_work: torch.Ten
         part[0] = n_take
         part[1] = e.sum()
         part[2] = (e > 0).sum()
-        part[3] = local_work[:n_take].to(torch.int64).sum()
+        part[3] = (local_work[:n_take].to(torch.int64) & 0xFFFF).sum()
     if ws > 1:
         dist.all_reduce(part, op=dist.ReduceOp.SUM)
     p = part.cpu().numpy()
@@ -190,8 +190,8 @@ def ber_point(engine, *, M: int, ebn0_db: float, payload_len: int, coded_len: in
     while not state.done and chunk_begin < max_frames:
         chunk = min(chunk, max_frames - chunk_begin)
         lb, ln = shard_range(chunk, rank, ws)
-        err = torch.zeros(ln, dtype=torch.uint8, device=engine.dev)
-        work = torch.zeros(ln, dtype=torch.uint8, device=engine.dev)
+        err = torch.zeros(ln, dtype=torch.int16, device=engine.dev)     # u16 on the device side: exact per-frame counts
+        work = torch.zeros(ln, dtype=torch.int16, device=engine.dev)
         counters = torch.zeros(NCOUNTERS, dtype=torch.int64, device=engine.dev)
         if ln > 0:
             engine.sweep(counters, M=M, noise_var=nv, n_frames=ln, frame_begin=chunk_begin + lb, seed=seed,

@@ -135,8 +135,8 @@ def test_sweep_equals_channel_plus_oracle(engines, Z, kcrc, poly, E):
     ref = O.ldpc_decode_batch(np.array([O.ldpc_derate_match(l, n) for l in llr]), H, 20, 0.8)
     be = (ref["hard"][:, :kp] != payload).sum(axis=1)
     counters = torch.zeros(16, dtype=torch.int64, device="cuda")
-    fbe = torch.zeros(B, dtype=torch.uint8, device="cuda")
-    fw = torch.zeros(B, dtype=torch.uint8, device="cuda")
+    fbe = torch.zeros(B, dtype=torch.int16, device="cuda")
+    fw = torch.zeros(B, dtype=torch.int16, device="cuda")
     eng.sweep(counters, noise_var=nv, n_frames=B, seed=11, stream_id=3, frame_bit_errors=fbe, frame_work=fw)
     c = counters.cpu().numpy()
     assert c[0] == B and c[1] == int((be > 0).sum()) and c[2] == int(be.sum()) and c[7] == int(ref["iters_used"].sum())

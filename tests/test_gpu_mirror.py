@@ -196,7 +196,7 @@ def test_ber_sweep_stop_rule_is_the_sequential_loop(tmp_path):
     row = R.run(args)[0]
     eng = engine_for(128, construct_info_set(128, 88), "0x1864CFB")
     n = 1 << 16
-    err = torch.zeros(n, dtype=torch.uint8, device=eng.dev)
+    err = torch.zeros(n, dtype=torch.int16, device=eng.dev)
     cnt = torch.zeros(16, dtype=torch.int64, device=eng.dev)
     eng.sweep(cnt, M=4, noise_var=mc.ber_noise_var(2.0, 64, 128), n_frames=n, seed=0, stream_id=0, k_payload=64,
               frame_error_mode=1, bit_error_span=64, frame_bit_errors=err)

@@ -129,7 +129,7 @@ def test_nr_sweep_and_ber_point(eng):
     e.set_rate_matching(256)
     nv = mc.ber_noise_var(3.0, 64, 256)
     n = 4000
-    err = torch.zeros(n, dtype=torch.uint8, device=e.dev)
+    err = torch.zeros(n, dtype=torch.int16, device=e.dev)
     c = torch.zeros(16, dtype=torch.int64, device=e.dev)
     e.sweep(c, M=4, noise_var=nv, n_frames=n, seed=2, stream_id=4, k_payload=64, frame_error_mode=1, bit_error_span=64,
             frame_bit_errors=err)
@@ -137,7 +137,7 @@ def test_nr_sweep_and_ber_point(eng):
     assert llr.shape == (n, 256)
     out = e.scl_decode(llr, 4)
     be = (out["best_bits"][:, :64] != msg[:, :64]).sum(dim=1)
-    assert torch.equal(be.to(torch.uint8), err)
+    assert torch.equal(be.to(torch.int16), err)
     c = c.cpu().numpy()
     assert c[2] == int(be.sum()) and c[1] == int((be > 0).sum())
     # the oracle decodes the very same rate-matched LLRs to the same words (except flagged ties)
@@ -220,3 +220,27 @@ def test_fer_matches_oracle_on_reference_channel(eng, g128, M, snr):
     # bit errors come in bursts (a wrong frame has ~10 wrong bits): scale sigma by the frame-level dispersion
     assert abs(ref["ber_scl"] - est["ber_scl"]) < 4 * est["ber_scl"] / math.sqrt(max(est["fer_scl"] * n_ref, 1))
     assert abs(ref["work"] - est["work"]) < 0.05 * max(est["work"], 1e-3) + 4e-3
+
+
+def test_frame_bit_errors_exact_above_255():
+    """N = 512, K = 488 + 24 (rate 1): at a hopeless operating point every second payload bit is wrong, i.e. 244 +- 11
+    errors per frame -- many frames carry > 255; the u16 per-frame counters (and hence run_ber_sweep's adaptive stop)
+    must report them exactly (round 1 clamped at 255)."""
+    from polar_code_b200.engine import PolarEngine, construct_info_set
+    from polar_code_b200 import montecarlo as mc
+    kp = 488
+    e = PolarEngine(512, construct_info_set(512, 512), CRC24)
+    nv = mc.ber_noise_var(-20.0, kp, 512)
+    n = 2048
+    err = torch.zeros(n, dtype=torch.int16, device=e.dev)
+    c = torch.zeros(16, dtype=torch.int64, device=e.dev)
+    e.sweep(c, M=2, noise_var=nv, n_frames=n, seed=5, stream_id=1, k_payload=kp, frame_error_mode=1, bit_error_span=kp,
+            frame_bit_errors=err)
+    msg, llr = e.channel(noise_var=nv, n_frames=n, seed=5, stream_id=1, k_payload=kp)
+    out = e.scl_decode(llr, 2)
+    be = (out["best_bits"][:, :kp] != msg[:, :kp]).sum(dim=1)
+    assert int((be > 255).sum()) > 20, "operating point too benign for this test"
+    assert torch.equal(be.to(torch.int64), err.to(torch.int64) & 0xFFFF)
+    assert int(c[2]) == int(be.sum())
+    with pytest.raises(ValueError):
+        e.sweep(c, M=2, noise_var=nv, n_frames=n, k_payload=kp, frame_bit_errors=torch.zeros(n, dtype=torch.uint8, device=e.dev))

@@ -45,8 +45,8 @@ def _chunked(err, work, payload_len, err_cap, bits_cap, first_chunk, rank=0, wor
     while not state.done and begin < max_frames:
         chunk = min(chunk, max_frames - begin)
         lb, ln = mc.shard_range(chunk, rank, world)
-        e = torch.from_numpy(err[begin + lb: begin + lb + ln].astype(np.uint8))
-        w = torch.from_numpy(work[begin + lb: begin + lb + ln].astype(np.uint8))
+        e = torch.from_numpy(err[begin + lb: begin + lb + ln].astype(np.int16))
+        w = torch.from_numpy(work[begin + lb: begin + lb + ln].astype(np.int16))
         state = mc.adaptive_cut(state, e, w, begin + lb, begin, chunk, payload_len, err_cap, bits_cap)
         begin += chunk
         chunk *= 2
@@ -64,6 +64,20 @@ def test_adaptive_cut_equals_sequential_loop(payload_len, err_cap, bits_cap, fir
     work = rng.integers(0, 9, n)
     want = _sequential(err, work, payload_len, err_cap, bits_cap)
     got = _chunked(err, work, payload_len, err_cap, bits_cap, first_chunk)
+    assert (got.frames, got.bit_errors, got.frame_errors, got.work_sum) == \
+        (want["frames"], want["bit_errors"], want["frame_errors"], want["work"])
+
+
+def test_adaptive_cut_counts_above_255_exactly():
+    """K_payload = 300 (N = 512): a badly failed frame carries more than 255 payload errors; the per-frame counters
+    are 16-bit so the prefix sums of the stopping rule stay exact (round-1 clamp at 255 undercounted)."""
+    rng = np.random.default_rng(7)
+    n = 4000
+    err = (rng.random(n) < 0.05) * rng.integers(200, 301, n)
+    work = rng.integers(0, 400, n)
+    assert err.max() > 255 and work.max() > 255
+    want = _sequential(err, work, 300, 20000, 1e9)
+    got = _chunked(err, work, 300, 20000, 1e9, 64)
     assert (got.frames, got.bit_errors, got.frame_errors, got.work_sum) == \
         (want["frames"], want["bit_errors"], want["frame_errors"], want["work"])
 
