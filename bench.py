@@ -45,6 +45,18 @@ def noise_var(snr_db: float) -> float:
     return 1.0 / (2.0 * (K / N) * 10 ** (snr_db / 10.0))   # run_fer_sweep.py:62-64
 
 
+def ncu_constants() -> dict:
+    """Per-frame constants of the dominant kernel measured with ncu and tracked under profiles/ (written by
+    scripts/ncu_summary.py --json from the capture of the SAME build; the roofline lines name the file they come from)."""
+    p = ROOT / "profiles" / "r02_constants.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        k = d.get("decode_kernel_M4", {})
+        if {"warp_instr_per_frame", "issue_slots_busy_pct", "dram_bytes_per_frame"} <= set(k):
+            return {**k, "file": "profiles/r02_constants.json"}
+    return {"warp_instr_per_frame": None, "issue_slots_busy_pct": None, "dram_bytes_per_frame": None, "file": None}
+
+
 def peaks() -> dict:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -300,35 +312,68 @@ def main() -> None:
     e2e_value = world * Be * Ksteps / (e2e_ms * 1e-3)
     assert torch.equal(h_bits.to(dev), best_bits[:Be]), "host-buffer path and device path disagree"
 
-    NCU_WARP_INSTR_PER_FRAME = 2722    # smsp__inst_executed.sum / frames of decode_kernel<4,7> (ncu metrics pass of the final build; full capture: profiles/r01_v9_decode_kernel_metrics.txt, 2 777)
     # ---- roofline -------------------------------------------------------------------------------------
     pk = peaks()
+    nc = ncu_constants()              # ncu constants of this build's decode_kernel<4,7> (profiles/r02_constants.json)
     ms_kernel = ms / Ksteps            # one decode_kernel launch per step, timed with CUDA events on its stream
     ach_gbs = HBM_BYTES_PER_FRAME * B / (ms_kernel * 1e-3) / 1e9
-    # ncu (profiles/r01_v9_decode_kernel_metrics.txt, 1 Mi-frame launch): dram read 584 B + write 81 B per frame,
-    # i.e. the algorithmic bytes (the scratch is pinned in L2 by an access-policy window and never reaches HBM);
-    # scaled here to this launch's B.
     roofline = {"bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / pk["hbm_gbs"],
-                "traffic": 665 * B, "traffic_source": "ncu dram__bytes per frame of a 1 Mi-frame launch x B", "peak_source": pk["source"],
+                "traffic": (nc["dram_bytes_per_frame"] * B) if nc["dram_bytes_per_frame"] else None,
+                "traffic_source": f"ncu dram__bytes per frame of a 1 Mi-frame launch x B ({nc['file']})", "peak_source": pk["source"],
                 "algorithmic_bytes_per_frame": HBM_BYTES_PER_FRAME,
                 "note": "decode_kernel<4,7> is SM-issue bound, not HBM bound (SURVEY 8(d)): see roofline_issue and profiles/"}
     lane_ops = ELEM_OPS[M] * B / (ms_kernel * 1e-3)
     sm_clock = (clocks.get("sm_mhz") or pk["sm_max_mhz"]) * 1e6
     props = torch.cuda.get_device_properties(dev)
     peak_max = props.multi_processor_count * 128 * pk["sm_max_mhz"] * 1e6
+    wipf = nc["warp_instr_per_frame"]
     roofline_issue = {"bound": "issue", "achieved": lane_ops, "unit": "element-ops/s (W_fg + W_pm = %d per frame)" % ELEM_OPS[M],
                       "peak": peak_max, "frac": lane_ops / peak_max,
                       "peak_at_measured_clock": props.multi_processor_count * 128 * sm_clock,
                       "frac_at_measured_clock": lane_ops / (props.multi_processor_count * 128 * sm_clock),
-                      "ncu_issue_slots_busy_pct": 75.6, "ncu_warp_instructions_per_frame": NCU_WARP_INSTR_PER_FRAME,
-                      "issue_slot_frac_live": NCU_WARP_INSTR_PER_FRAME * B / (ms_kernel * 1e-3) / (props.multi_processor_count * 4 * sm_clock),
-                      "note": "SURVEY 8(d) definition (algorithmic element-ops / lane-op peak); the kernel itself keeps 76% of the "
-                              "issue slots busy (ncu, profiles/r01_v9_*; issue_slot_frac_live = ncu warp-instructions per frame x "
-                              "this run's frames/s / (SMs x 4 schedulers x clock)) -- the gap is per-phase list management, not idle hardware"}
+                      "ncu_issue_slots_busy_pct": nc["issue_slots_busy_pct"], "ncu_warp_instructions_per_frame": wipf,
+                      "ncu_source": nc["file"],
+                      "issue_slot_frac_live": (wipf * B / (ms_kernel * 1e-3) / (props.multi_processor_count * 4 * sm_clock)) if wipf else None,
+                      "note": "SURVEY 8(d) definition (algorithmic element-ops / lane-op peak); issue_slot_frac_live = ncu "
+                              "warp-instructions per frame (profiles/) x this run's frames/s / (SMs x 4 schedulers x clock) -- "
+                              "the gap between the two is per-phase list management, not idle hardware"}
+
+    # ---- e2e ceiling: bare pinned H2D copies of the same buffers in the same chunks on all ranks at once -------
+    chunk = 1 << 16
+    d_sink = torch.empty((chunk, N), dtype=torch.float32, device=dev)
+    side = torch.cuda.Stream(device=dev)
+
+    def h2d_only():
+        with torch.cuda.stream(side):
+            for lo in range(0, Be, chunk):
+                n = min(chunk, Be - lo)
+                d_sink[:n].copy_(h_llr[lo:lo + n], non_blocking=True)
+
+    h2d_only(); side.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(3, Ksteps // 4)):
+        h2d_only()
+    side.synchronize()
+    h2d_ms = (time.perf_counter() - t0) * 1e3 / max(3, Ksteps // 4)
+    barrier()
+    if world > 1:
+        t = torch.tensor([h2d_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        h2d_ms = float(t.item())
+    h2d_gbs_per_gpu = Be * N * 4 / (h2d_ms * 1e-3) / 1e9
+    e2e_ceiling = {"h2d_ceiling_gbs_per_gpu": h2d_gbs_per_gpu, "h2d_ceiling_gbs_total": h2d_gbs_per_gpu * world,
+                   "h2d_ceiling_frames_per_s": world * Be / (h2d_ms * 1e-3),
+                   "how": "concurrent cudaMemcpyAsync of the same pinned LLR buffer in 2^16-frame chunks on every rank, nothing else running"}
 
     extras = {}
     if not args.no_extras and rank == 0 and world == 1:      # informational legs only on the single-GPU run
         extras = extra_legs(eng, llr, msg, dev, B)
+    # BASELINE config 5 at every N: DL-SCL M=8, 8 retries, shipped beta_M8, frames sharded over the ranks, counters
+    # all-reduced (weak scaling: fixed frames per GPU), timed as the max over ranks
+    scale_leg = None
+    if not args.no_extras:
+        scale_leg = dlscl_scale_leg(eng, dev, rank, world, barrier, min(B, 1 << 21))
 
     cb = cpu_baseline(args.cpu_sample) if (rank == 0 and world == 1) else None
 
@@ -340,7 +385,7 @@ def main() -> None:
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": Be * N * 4, "d2h_bytes_per_step": Be * (K + 1 + 4),
                     "rank0_cpu_affinity": numa_cpus,
                     "frames_per_step_per_gpu": Be, "ms_per_step": e2e_ms / Ksteps,
-                    "call": "pb200_scl_decode_host (pinned host LLRs -> best_bits, crc_ok, flags on the host)"},
+                    "call": "pb200_scl_decode_host (pinned host LLRs -> best_bits, crc_ok, flags on the host)", **e2e_ceiling},
             "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "roofline_issue": roofline_issue,
             "kernel": eng.kernel_info(M),
             "check": {"fer_vs_sent": fer, "crc_fail_rate": crc_fail, "near_tie_flag_rate": tie_frac},
@@ -349,18 +394,63 @@ def main() -> None:
             line["cpu_baseline"] = cb
         if extras:
             line["extras"] = extras
+        if scale_leg:
+            line["config5_dlscl_M8"] = scale_leg
         print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _golden_beta(M: int, dev):
+    import torch
+    g = np.load(ROOT / "tests" / "golden" / "scl_p128.npz")       # holds the reference's checkpoints/beta_M{M}.npy
+    return torch.as_tensor(g[f"beta_M{M}"], device=dev)
+
+
+def dlscl_scale_leg(eng, dev, rank, world, barrier, frames_per_gpu) -> dict:
+    """BASELINE configs[4]: fused Philox channel + SCL M=8 + DL-SCL (8 retries, shipped beta_M8) + counters at 5.0 dB."""
+    import torch
+    import torch.distributed as dist
+    beta = _golden_beta(8, dev)
+    counters = torch.zeros(16, dtype=torch.int64, device=dev)
+    nv = noise_var(5.0)
+
+    def run(rep):
+        eng.sweep(counters, M=8, noise_var=nv, n_frames=frames_per_gpu, frame_begin=(rep * world + rank) * frames_per_gpu, seed=5,
+                  stream_id=50, k_payload=KP, retries=8, beta=beta)
+        if world > 1:
+            dist.all_reduce(counters)
+
+    run(0); run(1)
+    counters.zero_()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record()
+    for r in range(reps):
+        run(2 + r)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / reps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    c = counters.cpu().numpy()
+    return {"frames_per_s": world * frames_per_gpu / (ms * 1e-3), "frames_per_step_per_gpu": frames_per_gpu, "snr_db": 5.0,
+            "beta": "checkpoints/beta_M8.npy (tests/golden/scl_p128.npz)", "retries": 8, "ms_per_step": ms,
+            "note": "counters are all-reduced every step, so with N ranks they hold N x the frames of the timed steps"}
+
+
 def extra_legs(eng, llr, msg, dev, B) -> dict:
     """Other BASELINE configs, timed the same way on rank 0 (informational; not the headline)."""
     import torch
+    from polar_code_b200.engine import PolarEngine, construct_info_set
+    from polar_code_b200 import montecarlo as mc
     out = {}
 
     def time_it(fn, reps=3):
-        fn()
+        fn(); fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -372,20 +462,38 @@ def extra_legs(eng, llr, msg, dev, B) -> dict:
 
     Bx = min(B, 1 << 21)
     x = llr[:Bx]
-    for m in (1, 8):
+    for m in (1, 8):                                                      # configs[1]
         ms = time_it(lambda: eng.scl_decode(x, m, want=("best_bits", "crc_ok", "flags")))
         out[f"scl_M{m}_frames_per_s"] = Bx / (ms * 1e-3)
     ms = time_it(lambda: eng.sc_decode(x))
     out["sc_frames_per_s"] = Bx / (ms * 1e-3)
+    # decode_scl's FULL output set (scl.py:203-209): all M candidates, metrics and info_llrs
+    xs = x[: 1 << 19]
+    ms = time_it(lambda: eng.scl_decode(xs, M, want=("cand", "metrics", "info_llrs", "n_cand", "best_idx", "best_bits", "crc_ok", "flags")))
+    out["scl_M4_full_outputs_frames_per_s"] = xs.shape[0] / (ms * 1e-3)
     # fused Monte-Carlo sweep (Philox channel + SCL M=4 + counters), 5.0 dB
     counters = torch.zeros(16, dtype=torch.int64, device=dev)
     ms = time_it(lambda: eng.sweep(counters, M=M, noise_var=noise_var(5.0), n_frames=Bx, seed=1, stream_id=2, k_payload=KP))
     out["fused_sweep_M4_frames_per_s"] = Bx / (ms * 1e-3)
-    # DL-SCL M=4, 8 retries, |L0| ranking (beta=None), 4.0 dB and 5.0 dB
+    # configs[2] / configs[4]: DL-SCL, 8 retries, with the reference's shipped beta (and, for comparison, |L0| ranking)
+    for m, snrs in ((4, (4.0, 5.0)), (8, (4.0, 5.0))):
+        beta = _golden_beta(m, dev)
+        for snr in snrs:
+            counters.zero_()
+            ms = time_it(lambda: eng.sweep(counters, M=m, noise_var=noise_var(snr), n_frames=Bx, seed=1, stream_id=3, k_payload=KP,
+                                           retries=8, beta=beta))
+            out[f"fused_dlscl_M{m}_r8_beta_{snr}dB_frames_per_s"] = Bx / (ms * 1e-3)
     for snr in (4.0, 5.0):
         counters.zero_()
         ms = time_it(lambda: eng.sweep(counters, M=M, noise_var=noise_var(snr), n_frames=Bx, seed=1, stream_id=3, k_payload=KP, retries=8))
-        out[f"fused_dlscl_M4_r8_{snr}dB_frames_per_s"] = Bx / (ms * 1e-3)
+        out[f"fused_dlscl_M4_r8_nobeta_{snr}dB_frames_per_s"] = Bx / (ms * 1e-3)
+    # configs[3]: NR rate-matched sweep, A(128,88) = 64 payload + CRC-24, E = 256, SCL M=4, Eb/N0 3.0 dB
+    nr = PolarEngine(N, construct_info_set(N, 88), CRC24, device=dev.index)
+    nr.set_rate_matching(256)
+    counters.zero_()
+    ms = time_it(lambda: nr.sweep(counters, M=M, noise_var=mc.ber_noise_var(3.0, 64, 256), n_frames=Bx, seed=1, stream_id=4, k_payload=64,
+                                  frame_error_mode=1, bit_error_span=64))
+    out["fused_nr_E256_K88_M4_frames_per_s"] = Bx / (ms * 1e-3)
     return out
 
 

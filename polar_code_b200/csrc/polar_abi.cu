@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <map>
+#include <mutex>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -135,12 +136,12 @@ struct pb200_engine {
     size_t llr_store_bytes = 0;
     float* d_abs_store = nullptr;         // |L0| rows of frames in the DL-SCL retry queue
     size_t abs_store_bytes = 0;
+    double* d_beta64 = nullptr;           // the caller's beta widened to fp64 for the current call [K,K]
     // per-warp global scratch of the decode kernels, one buffer per stream: kernels of one engine that are
     // enqueued on different streams may overlap on the device and must not share tree rows
     std::map<cudaStream_t, std::pair<unsigned char*, size_t>> scratch;
-    // L2 residency control of the scratch (pin_scratch_in_l2)
-    int l2_window_max = -1, l2_persist_max = 0;
-    bool l2_limit_set = false;
+    // L2 residency control of the scratch (pin_scratch_in_l2): -1 = not probed, -2 = switched off by the user
+    int l2_window_max = -1;
     std::map<cudaStream_t, std::pair<unsigned char*, size_t>> l2_window;
 };
 int sweep_build_tables(pb200_engine* e);
@@ -255,7 +256,7 @@ extern "C" void pb200_destroy(pb200_engine* e) {
     cudaSetDevice(e->device);
     cudaFree(e->d_info_pos); cudaFree(e->d_info_mask); cudaFree(e->d_crc_tab); cudaFree(e->d_rm_src); cudaFree(e->d_rm_cnt); cudaFree(e->d_tx_src);
     for (auto& kv : e->enc_tabs) cudaFree(kv.second);
-    cudaFree(e->d_llr_store); cudaFree(e->d_abs_store); cudaFree(e->d_rm_dst);
+    cudaFree(e->d_llr_store); cudaFree(e->d_abs_store); cudaFree(e->d_rm_dst); cudaFree(e->d_beta64);
     for (auto& kv : e->scratch) cudaFree(kv.second.first); cudaFree(e->d_q[0]); cudaFree(e->d_q[1]); cudaFree(e->d_q_counts);
     for (int i = 0; i < 3; ++i) {
         if (e->hs[i]) cudaStreamDestroy(e->hs[i]);
@@ -270,9 +271,8 @@ extern "C" int pb200_set_rate_matching(pb200_engine* e, int E) {
     if (E < 0) return fail(PB200_EINVAL, "E must be >= 0");
     CUDA_TRY(cudaSetDevice(e->device));
     const int N = e->code.N;
-    cudaFree(e->d_tx_src);
-    e->d_tx_src = nullptr;
-    std::vector<int16_t> rm(N), rd(N);
+    // 1. all host tables first (nothing of the engine is touched until every check and upload has succeeded)
+    std::vector<int16_t> rm(N), rd(N), tx;
     std::vector<int8_t> rcnt(N, 1);
     if (E == 0) {
         for (int i = 0; i < N; ++i) { rm[i] = (int16_t)i; rd[i] = (int16_t)i; }
@@ -292,17 +292,42 @@ extern "C" int pb200_set_rate_matching(pb200_engine* e, int E) {
         }
         for (int p = 0; p < N; ++p) rd[p] = (int16_t)(order[p] < N ? order[p] : -1);
         // transmit side: interleaved[k] = code[order[k]] or pad -1 (:17-21); rate_match: first E of the tiling (:8-16)
-        std::vector<int16_t> tx(E);
+        tx.resize(E);
         for (int t = 0; t < E; ++t) {
             const int k = (E <= total) ? t : (t % total);
             tx[t] = (int16_t)(order[k] < N ? order[k] : -1);
         }
-        CUDA_TRY(cudaMalloc((void**)&e->d_tx_src, (size_t)E * 2));
-        CUDA_TRY(cudaMemcpy(e->d_tx_src, tx.data(), (size_t)E * 2, cudaMemcpyHostToDevice));
     }
-    CUDA_TRY(cudaMemcpy(e->d_rm_src, rm.data(), (size_t)N * 2, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(e->d_rm_dst, rd.data(), (size_t)N * 2, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(e->d_rm_cnt, rcnt.data(), (size_t)N, cudaMemcpyHostToDevice));
+    // 2. the engine must be idle: kernels of earlier calls (on any stream) may still read the tables
+    CUDA_TRY(cudaDeviceSynchronize());
+    int16_t* new_tx = nullptr;
+    if (E > 0) {
+        CUDA_TRY(cudaMalloc((void**)&new_tx, (size_t)E * 2));
+        if (cudaMemcpy(new_tx, tx.data(), (size_t)E * 2, cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaFree(new_tx);
+            return fail(PB200_ECUDA, "upload of the transmit table failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+    }
+    // 3. fixed-size tables are overwritten in place; on a failure the engine falls back to "no rate matching" with
+    //    consistent identity tables instead of a half-updated state
+    const bool ok = cudaMemcpy(e->d_rm_src, rm.data(), (size_t)N * 2, cudaMemcpyHostToDevice) == cudaSuccess &&
+                    cudaMemcpy(e->d_rm_dst, rd.data(), (size_t)N * 2, cudaMemcpyHostToDevice) == cudaSuccess &&
+                    cudaMemcpy(e->d_rm_cnt, rcnt.data(), (size_t)N, cudaMemcpyHostToDevice) == cudaSuccess;
+    cudaFree(e->d_tx_src);
+    e->d_tx_src = nullptr;
+    if (!ok) {
+        const char* why = cudaGetErrorString(cudaGetLastError());
+        cudaFree(new_tx);
+        std::vector<int16_t> id(N);
+        for (int i = 0; i < N; ++i) id[i] = (int16_t)i;
+        std::vector<int8_t> one(N, 1);
+        cudaMemcpy(e->d_rm_src, id.data(), (size_t)N * 2, cudaMemcpyHostToDevice);
+        cudaMemcpy(e->d_rm_dst, id.data(), (size_t)N * 2, cudaMemcpyHostToDevice);
+        cudaMemcpy(e->d_rm_cnt, one.data(), (size_t)N, cudaMemcpyHostToDevice);
+        e->tb.E = 0;
+        return fail(PB200_ECUDA, "upload of the rate-matching tables failed (%s); rate matching is now off", why);
+    }
+    e->d_tx_src = new_tx;
     e->tb.E = E;
     return PB200_OK;
 }
@@ -311,7 +336,8 @@ extern "C" int pb200_set_rate_matching(pb200_engine* e, int E) {
 // Kernel selection
 // ---------------------------------------------------------------------------------------------------
 static const void* pick_decode(int n, int MP, bool forced, bool metric) {
-    return n <= 7 ? pb_decode_kernel_7(MP, forced, metric) : pb_decode_kernel_9(MP, forced, metric);
+    if (n == 7) return pb_decode_kernel_7s(MP, forced, metric);      // the headline geometry N = 128: static code length
+    return n < 7 ? pb_decode_kernel_7(MP, forced, metric) : pb_decode_kernel_9(MP, forced, metric);
 }
 
 static int round_mp(int M) { return M <= 1 ? 1 : M <= 2 ? 2 : M <= 4 ? 4 : 8; }
@@ -346,16 +372,22 @@ static int ensure_scratch(pb200_engine* e, cudaStream_t st, size_t warps, int MP
 // Keep the dense tree/channel scratch of a launch resident in L2 (it is re-written and re-read every few microseconds)
 // while everything else the stream touches -- the LLR rows in, the decisions out -- keeps the normal policy:
 // an access-policy window over the scratch with the persisting property, backed by an L2 set-aside.  Best effort
-// (older drivers / MIG slices without the feature just run without it).  Only the list kernels (MP >= 2) ask for it:
-// the thread-per-frame kernels (SC / M = 1) re-read 32 channel rows per warp at phase N/2 and are faster when the whole
-// L2 serves those rows (measured: 1.08e9 vs 0.65e9 frames/s), so a launch of theirs drops the window again.
-// PB200_L2_PIN=0 in the environment switches the feature off.
+// (older drivers / MIG slices without the feature just run without it).  Only the list kernels (MP >= 2) ask for it;
+// a thread-per-frame launch (SC / M = 1) clears the window of ITS stream only.
+// The set-aside (cudaLimitPersistingL2CacheSize) is DEVICE-wide state: it is taken once per device by the first engine
+// that needs it, recorded in process-global state and never changed from a launch path again -- other engines, streams
+// and libraries in the process keep whatever residency they arranged.  PB200_L2_PIN=0 switches the feature off;
+// PB200_L2_SETASIDE_MB caps the set-aside (default: all the device allows) for processes that share the GPU's L2.
+struct L2DeviceState { bool probed = false, limit_set = false; int window_max = 0, persist_max = 0; };
+static L2DeviceState g_l2[64];
+static std::mutex g_l2_mutex;
+
 static void pin_scratch_in_l2(pb200_engine* e, cudaStream_t st, unsigned char* scratch, size_t bytes, bool enable) {
     if (e->l2_window_max == -1) {
         const char* env = getenv("PB200_L2_PIN");
-        if (env && env[0] == '0') e->l2_window_max = -2;      // disabled by the user
+        e->l2_window_max = (env && env[0] == '0') ? -2 : 0;      // -2: disabled by the user
     }
-    if (e->l2_window_max == -2) return;
+    if (e->l2_window_max == -2 || e->device < 0 || e->device >= 64) return;
     if (!enable) {
         auto it = e->l2_window.find(st);
         if (it == e->l2_window.end() || it->second.first == nullptr) return;
@@ -366,34 +398,37 @@ static void pin_scratch_in_l2(pb200_engine* e, cudaStream_t st, unsigned char* s
         v.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
         v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
         if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
-        if (cudaCtxResetPersistingL2Cache() != cudaSuccess) cudaGetLastError();
-        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0) != cudaSuccess) cudaGetLastError();   // give the set-aside back
-        e->l2_limit_set = false;
         it->second = {nullptr, 0};
         return;
     }
-    if (e->l2_window_max < 0) {
-        int max_win = 0, max_persist = 0;
-        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, e->device);
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, e->device);
-        e->l2_window_max = max_win;
-        e->l2_persist_max = max_persist;
+    L2DeviceState ds;
+    {
+        std::lock_guard<std::mutex> lock(g_l2_mutex);
+        L2DeviceState& g = g_l2[e->device];
+        if (!g.probed) {
+            cudaDeviceGetAttribute(&g.window_max, cudaDevAttrMaxAccessPolicyWindowSize, e->device);
+            cudaDeviceGetAttribute(&g.persist_max, cudaDevAttrMaxPersistingL2CacheSize, e->device);
+            if (const char* cap = getenv("PB200_L2_SETASIDE_MB")) {
+                const long long mb = atoll(cap);
+                if (mb >= 0 && mb * (1ll << 20) < g.persist_max) g.persist_max = (int)(mb << 20);
+            }
+            g.probed = true;
+        }
+        if (g.window_max > 0 && g.persist_max > 0 && !g.limit_set) {
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)g.persist_max) != cudaSuccess) cudaGetLastError();
+            g.limit_set = true;
+        }
+        ds = g;
     }
-    if (e->l2_window_max <= 0 || e->l2_persist_max <= 0) return;
-    if (!e->l2_limit_set) {
-        // the whole set-aside the device allows: later launches of this engine may bring a larger scratch, and the
-        // window's hitRatio below is computed against this size
-        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)e->l2_persist_max) != cudaSuccess) cudaGetLastError();
-        e->l2_limit_set = true;
-    }
+    if (ds.window_max <= 0 || ds.persist_max <= 0) return;
     auto& cur = e->l2_window[st];
     if (cur.first == scratch && cur.second == bytes) return;
     cudaStreamAttrValue v{};
     v.accessPolicyWindow.base_ptr = scratch;
-    v.accessPolicyWindow.num_bytes = std::min(bytes, (size_t)e->l2_window_max);
-    v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)e->l2_persist_max / (double)std::max<size_t>(v.accessPolicyWindow.num_bytes, 1));
+    v.accessPolicyWindow.num_bytes = std::min(bytes, (size_t)ds.window_max);
+    v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)ds.persist_max / (double)std::max<size_t>(v.accessPolicyWindow.num_bytes, 1));
     v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;      // (streaming would evict the LLR rows before their second read at phase N/2)
+    v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
     if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
     cur = {scratch, bytes};
 }

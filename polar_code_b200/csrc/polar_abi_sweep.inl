@@ -110,16 +110,32 @@ static int check_sweep_cfg(pb200_engine* e, const pb200_sweep_cfg* c) {
     return PB200_OK;
 }
 
+static __global__ void widen_beta_kernel(const float* __restrict__ in, double* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)in[i];
+}
+
 // Shared driver: baseline launch + `retries` round launches over [frame_begin, frame_begin + n_frames).
 static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
     const int MP = round_mp(M);
+    a.beta64 = nullptr;
+    if (a.beta != nullptr && a.retries > 0) {
+        // flip.py:104-108 multiplies float64 |L0| by the float32 beta in float64: widen beta once per call (K^2 values)
+        // instead of once per multiply-add inside the retry kernel
+        const int kk = e->code.K * e->code.K;
+        if (!e->d_beta64) CUDA_TRY(cudaMalloc((void**)&e->d_beta64, (size_t)kk * sizeof(double)));
+        widen_beta_kernel<<<(kk + 255) / 256, 256, 0, st>>>(a.beta, e->d_beta64, kk);
+        CUDA_TRY(cudaGetLastError());
+        a.beta64 = e->d_beta64;
+    }
     const bool big = e->code.n > 7;
     Code code = e->code;
     code.M = M;
     // with retries the baseline pass records the leaf-LLR trace and writes |L0| of every queued frame (kind 2)
     const bool trace = a.retries > 0;
-    const void* base = big ? pb_sweep_kernel_9(MP, trace ? 2 : 0) : pb_sweep_kernel_7(MP, trace ? 2 : 0);
-    const void* round = big ? pb_sweep_kernel_9(MP, 1) : pb_sweep_kernel_7(MP, 1);
+    auto pick = [&](int kind) { return big ? pb_sweep_kernel_9(MP, kind) : code.n == 7 ? pb_sweep_kernel_7s(MP, kind) : pb_sweep_kernel_7(MP, kind); };
+    const void* base = pick(trace ? 2 : 0);
+    const void* round = pick(1);
     KernelCfg kb, kr{};
     int rc = choose_cfg(e, base, MP, trace ? 6 : 4, warp_bytes(MP, code.N, 0, false, trace ? code.K : 0) + acc_bytes(MP), &kb);
     if (rc) return rc;
@@ -130,11 +146,12 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
         rgrid = std::max(1, e->sms * kr.ctas_per_sm);
     }
     const int fpw = 32 / MP;
-    // pieces of >= 4 Mi frames: with retries every queued frame keeps its LLR row (N floats) in the store, so the
-    // worst case (every frame fails) is 4 Mi x N x 4 B = 2 GB for N = 128 -- allocated lazily, grown on demand
-    // With retries every piece ends in a tail in which the last frames run their (sequential) retries on a mostly idle
-    // GPU, so DL-SCL pieces are made as large as memory comfortably allows: up to 16 Mi frames (14 GB of queue, LLR and
-    // |L0| stores for N = 128 -- a B200 has 180 GB), less when less than four times that is free.
+    // Pieces of up to 4 Mi frames.  With retries every queued frame keeps its LLR row (N floats), its |L0| row (K floats)
+    // and a queue entry; the stores are sized for the worst case of a piece (every frame fails), i.e. 2.4 GB for 4 Mi frames
+    // of N = 128.  Every piece ends in a tail in which the last frames run their (sequential) retries on a mostly idle GPU,
+    // so DL-SCL pieces are made as large as memory comfortably allows: up to 16 Mi frames when four times the stores fit
+    // in free memory (a B200 has 180 GB), and DOWN to 64 Ki frames when they do not (small GPUs, MIG slices, a GPU shared
+    // with another workload) -- the sweep then runs in more pieces instead of failing in cudaMalloc.
     long long piece_max = 1ll << 22;
     if (a.retries > 0) {
         const size_t per_frame = (size_t)code.N * 4 + (size_t)code.K * 4 + entry_bytes(e);
@@ -142,6 +159,7 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
         if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
         const size_t have = free_b + e->llr_store_bytes + e->abs_store_bytes + e->q_bytes;    // what we hold already counts
         while (piece_max < (1ll << 24) && (size_t)(piece_max * 2) * per_frame * 4 <= have) piece_max *= 2;
+        while (piece_max > (1ll << 16) && (size_t)piece_max * per_frame * 2 > have) piece_max /= 2;
     }
     const long long total = a.n_frames, begin0 = a.frame_begin;
     const long long out_base = a.frame_begin;   // per-frame outputs are indexed by frame - frame_begin of the whole call

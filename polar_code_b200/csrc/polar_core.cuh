@@ -44,11 +44,20 @@ constexpr int kMaxWords = 16;         // N/32
 constexpr uint32_t kFull = 0xffffffffu;
 
 // Code description handed to every kernel by value (lives in the constant bank).
+// Kernels instantiated with a static code length (template parameter NS = log2 N, 0 = any) replace N and n by
+// compile-time constants: the schedule arithmetic of the phase loop (which tree height a phase recomputes, whether it
+// reads the channel rows, the width of the partial-sum words) folds away for the headline geometry N = 128.
 struct Code {
     int N, n, K, M;                   // code length, log2, info bits, list size (M <= MP)
     int crc_deg;                      // 0 = no CRC
     uint32_t info_mask[kMaxWords];    // bit phi set <=> phase phi is an information bit (index it with STATIC indices only)
 };
+
+template <int NS> __device__ __forceinline__ Code with_static_n(const Code& c) {
+    Code r = c;
+    if constexpr (NS > 0) { r.N = 1 << NS; r.n = NS; }
+    return r;
+}
 
 __device__ __forceinline__ float f_op(float a, float b) {
     // polar.py:122-123 : sign(a) sign(b) min(|a|,|b|)   (exact in fp32)
@@ -71,7 +80,11 @@ __device__ __forceinline__ float g_op_packed(float a, float b, uint32_t word, in
 // (Chebyshev-node fit, max relative error 5e-9; 1.6e-7 after fp32 Horner) -- as accurate as log1pf(expf()) in
 // fp32 (2.9e-7) at a third of the instructions; the t*q form keeps full relative accuracy as t -> 0.
 __device__ __forceinline__ float softplus_tail(float L) {
-    const float t = __expf(-fabsf(L));
+    // t = exp(-|L|) as one FMUL + MUFU.EX2 (ex2.approx.ftz: results below 2^-126, i.e. |L| > 87.3, flush to zero -- the
+    // reference's float64 tail is < 1.2e-38 there; two metrics that differ only by such tails compare as a tie here and
+    // the frame is flagged PB_FLAG_NEAR_TIE like any other near-tie)
+    float t;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(L) * -1.4426950408889634f));
     float q = -3.176057010e-03f;
     q = fmaf(q, t, 1.954252722e-02f);
     q = fmaf(q, t, -5.637361275e-02f);
@@ -216,6 +229,24 @@ __device__ __forceinline__ void stage_channel_rows(const WM& wm, int N, int lane
             const int t = it * 32 + lane, f = t & (FPW - 1), di = t / FPW;
             if (di < C) wm.chan[(c0 + di) * FPW + f] = tile[f * TS + di];
         }
+        __syncwarp();
+    }
+}
+// The common case: the FPW rows are CONTIGUOUS in memory (frames g*FPW .. g*FPW+FPW-1 of a [B, N] buffer), all valid and
+// N is a multiple of 32 -- no per-row pointers, no guards.
+template <int MP, typename WM>
+__device__ __forceinline__ void stage_channel_block(const WM& wm, int N, int lane, const float* rows) {
+    constexpr int FPW = 32 / MP, TS = 32 + MP;
+    float* tile = wm.ts;
+    const float* src = rows + lane;
+    float* dst = wm.chan + lane;
+    const float* trd = tile + (lane & (FPW - 1)) * TS + lane / FPW;       // tile[f * TS + di], di = it * MP + lane / FPW
+    for (int c0 = 0; c0 < N; c0 += 32) {
+#pragma unroll
+        for (int f = 0; f < FPW; ++f) tile[f * TS + lane] = src[(size_t)f * N + c0];
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < FPW; ++it) dst[c0 * FPW + it * 32] = trd[it * MP];
         __syncwarp();
     }
 }

@@ -34,37 +34,30 @@ struct ListDecoder {
             return;
         }
         if (n == 1) { a = chanf[0]; b = chanf[FPW]; return; }    // N = 2: the channel row is the pair
-        const int c = (phi == 0) ? n - 1 : __ffs(phi) - 1;       // first height produced (>= 1)
-        if (c == n - 1) {
-            // height n-1 straight from the staged channel rows (stride FPW): f at phi = 0, g at phi = N/2
-            if (phi == 0) {
-                switch (c) {
-#define PB_CASE(HH) case HH: if constexpr (HH < LOGMAX) TreeT::template produce<HH, 0, FPW>(chanf, p.bw, wm, lane, a, b); break;
-                    PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7) PB_CASE(8)
+        // first height produced: c = n-1 at phi = 0, else the number of trailing zeros of phi (>= 1)
+        // One case per height, everything inside it static: the slot field of P, the source row, the pointer update
+        // (heights 2..c live in the own slot afterwards).  Height n-1 comes straight from the staged channel rows
+        // (stride FPW): f at phi = 0, g at phi = N/2.
+        // (an if-chain on the bits of phi, most frequent height first -- height c is visited N / 2^(c+1) times per
+        //  frame -- is cheaper than the two-level jump table the compiler builds for a switch on c)
+#define PB_CASE(CC)                                                                                                   \
+    if ((phi & (1 << CC)) || (phi == 0 && CC == n - 1)) {                                                             \
+        if constexpr (CC < LOGMAX) {                                                                                  \
+            if (CC == n - 1) {                                                                                        \
+                if (phi == 0) TreeT::template produce<CC, 0, FPW>(chanf, p.bw, wm, lane, a, b);                       \
+                else TreeT::template produce<CC, 1, FPW>(chanf, p.bw, wm, lane, a, b);                                \
+            } else if constexpr (CC + 1 < LOGMAX) {                                                                   \
+                const uint32_t q = (p.P >> (4 * CC)) & 0xfu;         /* slot holding height CC+1 (field CC) */        \
+                const float* src = ((CC + 1 >= HS) ? wm.tg : wm.ts) + (((2 << CC) - 2) * 32) + gbase + q;             \
+                TreeT::template produce<CC, 1, 32>(src, p.bw, wm, lane, a, b);                                        \
+            }                                                                                                         \
+            constexpr uint32_t mask = (CC >= 8) ? 0xffffffffu : ((1u << (4 * CC)) - 1u);                              \
+            p.P = (p.P & ~mask) | ((slot * 0x11111111u) & mask);                                                      \
+        }                                                                                                             \
+        return;                                                                                                       \
+    }
+        PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7) PB_CASE(8)
 #undef PB_CASE
-                    default: break;
-                }
-            } else {
-                switch (c) {
-#define PB_CASE(HH) case HH: if constexpr (HH < LOGMAX) TreeT::template produce<HH, 1, FPW>(chanf, p.bw, wm, lane, a, b); break;
-                    PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7) PB_CASE(8)
-#undef PB_CASE
-                    default: break;
-                }
-            }
-        } else {
-            const uint32_t q = (p.P >> (4 * c)) & 0xfu;          // slot holding height c+1 (field c)
-            const float* src = ((c + 1 >= HS) ? wm.tg : wm.ts) + (((2 << c) - 2) * 32) + gbase + q;
-            switch (c) {
-#define PB_CASE(CC) case CC: if constexpr (CC + 1 < LOGMAX) TreeT::template produce<CC, 1, 32>(src, p.bw, wm, lane, a, b); break;
-                PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7)
-#undef PB_CASE
-                default: break;
-            }
-        }
-        // heights 2..c now live in the own slot
-        const uint32_t mask = (c >= 8) ? 0xffffffffu : ((1u << (4 * c)) - 1u);
-        p.P = (p.P & ~mask) | ((slot * 0x11111111u) & mask);
     }
 
     // scl.py:84-99 in packed form, for an ODD phase (at least one trailing one).
@@ -78,10 +71,9 @@ struct ListDecoder {
             else store_height<1, BW, 1>(p.bw, cw);
             return;
         }
-        const int t = __ffs(~phi) - 1;  // trailing ones of phi, >= 1
-        switch (t) {
+        // t = trailing ones of phi (>= 1): an if-chain on the bits of phi, shortest run first
 #define PB_CASE(TT)                                                                     \
-    case TT:                                                                            \
+    if (!(phi & (1 << TT))) {                                                           \
         if constexpr (TT <= LOGMAX) {                                                   \
             constexpr int CW = ((1 << TT) / 32) > 0 ? ((1 << TT) / 32) : 1;             \
             uint32_t cw[CW];                                                            \
@@ -90,11 +82,10 @@ struct ListDecoder {
                 _Pragma("unroll") for (int k = 0; k < CW; ++k) p.xh[k] = cw[k];        \
             } else if constexpr (TT < LOGMAX) store_height<TT, BW, CW>(p.bw, cw);       \
         }                                                                               \
-        break;
-            PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7) PB_CASE(8) PB_CASE(9)
+        return;                                                                         \
+    }
+        PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7) PB_CASE(8) PB_CASE(9)
 #undef PB_CASE
-            default: break;
-        }
     }
 
     // r += (x < y) for doubles: one DSETP + one predicated IADD
@@ -151,6 +142,8 @@ struct ListDecoder {
         // the four-fold body costs them more in instruction fetch than the dispatch it removes).
         auto phase = [&](const int phi, auto rc, const int half) {
             constexpr int R = decltype(rc)::value;
+            // info / force masks as shift registers: bit 0 is the current phase (reloaded every 32 phases, shifted by one
+            // at the end of every phase)
             if (R <= 0 || R == 10) {
                 if ((phi & 31) == 0) {
                     cur_info = __ldg(imask + (phi >> 5));     // (a dynamic index into the by-value Code would force it into local memory)
@@ -171,9 +164,11 @@ struct ListDecoder {
                 L = f_op(a, b);
             }
             else L = g_op_packed(a, b, p.bw[0], 0);              // u_{phi-1} sits in the height-0 field
-            const bool is_info = (cur_info >> (phi & 31)) & 1u;
-            const bool is_forced = FORCED && is_info && ((cur_fm >> (phi & 31)) & 1u);
-            const uint32_t forced_val = (cur_fv >> (phi & 31)) & 1u;
+            const bool is_info = cur_info & 1u;
+            const bool is_forced = FORCED && is_info && (cur_fm & 1u);
+            const uint32_t forced_val = cur_fv & 1u;
+            cur_info >>= 1;
+            if constexpr (FORCED) { cur_fm >>= 1; cur_fv >>= 1; }
             uint32_t bit = 0;
             if constexpr (!METRIC) {
                 // plain SC (polar.py:147-153): frozen -> 0 else L < 0

@@ -117,10 +117,14 @@ __device__ __forceinline__ void load_force(const Code& code, const int8_t* force
     }
 }
 
+#ifndef PB_LIST_THREADS
+#define PB_LIST_THREADS 1024
+#endif
 // N <= 128: compiled for 1024 threads per CTA, i.e. 64 registers -> 32 resident warps per SM (no spills for the plain
 // kernels, a few dozen bytes for the forced ones); N = 256 / 512 keep 16 partial-sum words per path and get 128 registers.
-template <int MP, int LOGMAX, bool FORCED, bool METRIC, int HS = DefaultHS<MP>::value>
-__global__ void __launch_bounds__(LOGMAX <= 7 ? 1024 : 512) decode_kernel(const Code code, const Tables tb, const DecodeArgs a) {
+template <int MP, int LOGMAX, bool FORCED, bool METRIC, int NS = 0, int HS = DefaultHS<MP>::value>
+__global__ void __launch_bounds__(LOGMAX <= 7 ? (MP > 1 ? PB_LIST_THREADS : 1024) : 512) decode_kernel(const Code code_, const Tables tb, const DecodeArgs a) {
+    const Code code = with_static_n<NS>(code_);
     using Dec = ListDecoder<MP, LOGMAX, FORCED, METRIC, HS>;
     using WM = WarpMem<MP, HS>;
     using PathT = typename Dec::PathT;
@@ -138,7 +142,8 @@ __global__ void __launch_bounds__(LOGMAX <= 7 ? 1024 : 512) decode_kernel(const 
         const int64_t frame = frame0 + lane / MP;
         const bool valid = frame < a.B;
         if (tb.E == 0) {
-            stage_channel_rows<MP>(wm, code.N, lane, [&](int f) -> const float* {
+            if (frame0 + FPW <= a.B && (code.N & 31) == 0) stage_channel_block<MP>(wm, code.N, lane, a.llr + frame0 * (int64_t)code.N);
+            else stage_channel_rows<MP>(wm, code.N, lane, [&](int f) -> const float* {
                 return frame0 + f < a.B ? a.llr + (frame0 + f) * (int64_t)a.in_len : nullptr; });
         } else load_channel<MP, WM>(code, tb, wm, a.llr, a.in_len, frame0, a.B, lane);
         const float* chanf = wm.chan + lane / MP;

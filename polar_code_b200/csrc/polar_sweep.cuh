@@ -72,7 +72,8 @@ struct SweepArgs {
     ChanCfg cc;
     int retries, run_scl, fe_mode;
     uint32_t be_mask[kMaxWords];   // phases whose bits are compared for bit errors
-    const float* beta;
+    const float* beta;             // caller's beta [K,K] f32 (null: |L0| ranking)
+    const double* beta64;          // the same matrix widened to fp64 once per call (no conversion inside the scoring loop)
     unsigned long long* counters;
     uint16_t* frame_bit_errors;   // exact per-frame counts (K <= 512, retries <= 65535)
     uint16_t* frame_work;
@@ -462,8 +463,9 @@ struct Sweep {
 // ---------------------------------------------------------------------------------------------------
 // TRACE (chosen when DL-SCL retries follow): the list decode records the leaf-LLR trace, and every frame that enters
 // the retry queue gets the |L0| vector of its best path written to abs_store (no SC replay anywhere in DL-SCL).
-template <int MP, int LOGMAX, bool TRACE = false, int HS = DefaultHS<MP>::value>
-__global__ void __launch_bounds__(PB_SWEEP_THREADS) sweep_kernel(const Code code, const Tables tb, const SweepArgs a) {
+template <int MP, int LOGMAX, bool TRACE = false, int NS = 0, int HS = DefaultHS<MP>::value>
+__global__ void __launch_bounds__(PB_SWEEP_THREADS) sweep_kernel(const Code code_, const Tables tb, const SweepArgs a) {
+    const Code code = with_static_n<NS>(code_);
     using S = Sweep<MP, LOGMAX, HS>;
     using WM = WarpMem<MP, HS>;
     using PathT = typename S::PathT;
@@ -557,8 +559,9 @@ __global__ void __launch_bounds__(PB_SWEEP_THREADS) sweep_kernel(const Code code
 // trace the previous list decode of that frame left behind (baseline: abs_store; retries: trace_walk) -- the leaf
 // LLRs are never recomputed by an SC replay.
 // ---------------------------------------------------------------------------------------------------
-template <int MP, int LOGMAX, int HS = 5>
-__global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_retry_kernel(const Code code, const Tables tb, const SweepArgs a) {
+template <int MP, int LOGMAX, int NS = 0, int HS = 5>
+__global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_retry_kernel(const Code code_, const Tables tb, const SweepArgs a) {
+    const Code code = with_static_n<NS>(code_);
     using S = Sweep<MP, LOGMAX, HS>;
     using WM = WarpMem<MP, HS>;
     using PathT = typename S::PathT;
@@ -628,40 +631,72 @@ __global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_retry_ker
         // rank_indices (flip.py:104-108): first untried index of argsort(|L0| @ beta) = argmin over untried
         double m1 = 1e300, m2 = 1e300;
         int a1 = 0x7fffffff;
+        auto offer = [&](double q, int j) {              // candidate score q of info index j (skipped when tried before)
+            uint32_t tw = 0;
 #pragma unroll
-        for (int w = 0; w < XW; ++w) {
-            if (w * 32 < K) {
-                double q[32 / MP];
+            for (int w = 0; w < XW; ++w) if (w == (j >> 5)) tw = tried[w];
+            if (j < K && !((tw >> (j & 31)) & 1u)) {
+                if (q < m1 || (q == m1 && j < a1)) { m2 = m1; m1 = q; a1 = j; }
+                else if (q < m2) m2 = q;
+            }
+        };
+        if (a.beta64 != nullptr && MP >= 4) {
+            // q = |L0| @ beta of the warp's frames on the FP64 tensor cores: D[8 x 8] += A[8 x 4] B[4 x 8]
+            // (mma.m8n8k4.f64).  Row r = lane / 4 of A and D belongs to the frame of lane 4r (MP = 4: one row per frame;
+            // MP = 8: two identical rows per frame), so every lane loads |L0| of ITS OWN frame and receives scores of
+            // its own frame: A[r][k] = |L0|[i0 + lane % 4], B[k][n] = beta[i0 + lane % 4][j0 + lane / 4], and the lane
+            // ends up with columns j0 + 2 (lane % 4) + {0, 1}.  128 DMMAs replace 4 096 load + convert + DFMA triples
+            // per retry (flip.py:104-108 is K^2 multiply-adds; the summation order inside a DMMA differs from numpy's
+            // BLAS order as any other order would -- scores closer than 2e-6 relative are flagged PB_FLAG_RANK_TIE).
+            const int kq = lane & 3, nq = lane >> 2;
+            for (int j0 = 0; j0 < K; j0 += 8) {
+                double c0 = 0.0, c1 = 0.0;
+                const bool bj = j0 + nq < K;
+                const double* bp = a.beta64 + j0 + nq;
+                for (int i0 = 0; i0 < K; i0 += 4) {
+                    const int i = i0 + kq;
+                    const double av = i < K ? (double)ab[i] : 0.0;
+                    const double bv = (i < K && bj) ? __ldg(bp + (size_t)i * K) : 0.0;
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                 : "+d"(c0), "+d"(c1) : "d"(av), "d"(bv));
+                }
+                offer(c0, j0 + 2 * kq);
+                offer(c1, j0 + 2 * kq + 1);
+            }
+        } else {
 #pragma unroll
-                for (int k = 0; k < 32 / MP; ++k) q[k] = 0.0;
-                if (a.beta) {
-                    for (int i = 0; i < K; ++i) {
-                        const double x = (double)ab[i];
+            for (int w = 0; w < XW; ++w) {
+                if (w * 32 < K) {
+                    double q[32 / MP];
+#pragma unroll
+                    for (int k = 0; k < 32 / MP; ++k) q[k] = 0.0;
+                    if (a.beta64) {
+                        for (int i = 0; i < K; ++i) {
+                            const double x = (double)ab[i];
+#pragma unroll
+                            for (int k = 0; k < 32 / MP; ++k) {
+                                const int j = w * 32 + slot + MP * k;
+                                if (j < K) q[k] += x * __ldg(&a.beta64[(size_t)i * K + j]);
+                            }
+                        }
+                    } else {
 #pragma unroll
                         for (int k = 0; k < 32 / MP; ++k) {
                             const int j = w * 32 + slot + MP * k;
-                            if (j < K) q[k] += x * (double)__ldg(&a.beta[(size_t)i * K + j]);
+                            if (j < K) q[k] = (double)ab[j];
                         }
                     }
-                } else {
 #pragma unroll
-                    for (int k = 0; k < 32 / MP; ++k) {
-                        const int j = w * 32 + slot + MP * k;
-                        if (j < K) q[k] = (double)ab[j];
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 32 / MP; ++k) {
-                    const int jj = slot + MP * k, j = w * 32 + jj;
-                    if (j < K && !((tried[w] >> jj) & 1u)) {
-                        if (q[k] < m1 || (q[k] == m1 && j < a1)) { m2 = m1; m1 = q[k]; a1 = j; }
-                        else if (q[k] < m2) m2 = q[k];
-                    }
+                    for (int k = 0; k < 32 / MP; ++k) offer(q[k], w * 32 + slot + MP * k);
                 }
             }
         }
+        // (tensor-core path, MP = 8: lanes l and l ^ 4 hold the SAME columns of the same frame -- reducing over them too
+        //  would make every best score its own runner-up)
+        const int red = (a.beta64 != nullptr && MP >= 4) ? 4 : MP;
 #pragma unroll
         for (int o = 1; o < MP; o <<= 1) {
+            if (o >= red) break;
             const double om1 = __shfl_xor_sync(kFull, m1, o), om2 = __shfl_xor_sync(kFull, m2, o);
             const int oa1 = __shfl_xor_sync(kFull, a1, o);
             if (om1 < m1 || (om1 == m1 && oa1 < a1)) { m2 = fmin(m1, om2); m1 = om1; a1 = oa1; }

@@ -54,8 +54,14 @@ def sweep_rows(args: argparse.Namespace) -> List[Dict[str, float]]:
     beta = np.load(args.beta) if args.beta else None
     if beta is not None and beta.shape != (cfg.K, cfg.K):
         raise ValueError("beta must be a square matrix matching abs_l0 length")
+    t_start = time.perf_counter()
     eng = engine_for(cfg.N, info_set, cfg.crc_poly)
     rank, _ = mc.world()
+    t_engine = time.perf_counter() - t_start
+    t_warm = mc.warm_up(eng, M=args.M, retries=args.retries, beta=beta, k_payload=payload_bits)
+    if rank == 0:                                 # start-up is reported apart from the per-point steady state
+        print(f"[b200] set-up: engine {t_engine:.3f} s + first launch {t_warm:.3f} s (kernel attributes, scratch, queues); "
+              f"the points below are steady state", file=sys.stderr)
     rows: List[Dict[str, float]] = []
     for snr_db in _snr_grid(args):
         t0 = time.perf_counter()

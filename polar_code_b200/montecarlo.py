@@ -9,6 +9,7 @@ CPU tests of this host logic).
 from __future__ import annotations
 
 import math
+import time
 import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
@@ -97,6 +98,21 @@ def fer_noise_var(snr_db: float, K: int, N: int) -> float:
 def ber_noise_var(ebn0_db: float, payload_bits: int, coded_bits: int) -> float:
     """run_ber_sweep.py:105-109 -- the CRC bits are overhead."""
     return 1.0 / (2.0 * (10 ** (ebn0_db / 10.0)) * (payload_bits / coded_bits))
+
+
+def warm_up(engine, *, M: int, retries: int, beta=None, k_payload: Optional[int] = None) -> float:
+    """First-launch set-up, paid once per process and configuration BEFORE the first timed point: kernel attribute /
+    occupancy queries, scratch and queue allocation, the L2 set-aside, module load of the kernels.  Runs one tiny
+    sweep (64 frames of a private Philox stream, counters discarded) and returns the seconds it took, so the CLIs can
+    report start-up separately from the steady-state frames/s (config 1 spends most of its
+    5 s wall time here)."""
+    t0 = time.perf_counter()
+    scratch = torch.zeros(NCOUNTERS, dtype=torch.int64, device=engine.dev)
+    kp = engine.K if k_payload is None else k_payload
+    engine.sweep(scratch, M=M, noise_var=1.0, n_frames=64, frame_begin=0, seed=0x5EED, stream_id=0xFFFF, retries=retries,
+                 run_scl=True, k_payload=kp, frame_error_mode=0, bit_error_span=engine.K, beta=beta)
+    torch.cuda.synchronize(engine.dev)
+    return time.perf_counter() - t0
 
 
 def fer_point(engine, *, M: int, snr_db: float, frames: int, seed: int, retries: int, beta=None,

@@ -11,13 +11,13 @@ args = sys.argv[1:]
 tp = args[0] if args and not args[0].startswith("--") else "4,7,false,true"
 kind = args[args.index("--kernel") + 1] if "--kernel" in args else "decode"
 inst = {"decode": f"template __global__ void pb::decode_kernel<{tp}>(const Code, const Tables, const DecodeArgs);",
-        "sweep": f"template __global__ void pb::sweep_kernel<{tp.split(',')[0]}, {tp.split(',')[1]}, false>(const Code, const Tables, const SweepArgs);",
-        "sweeptrace": f"template __global__ void pb::sweep_kernel<{tp.split(',')[0]}, {tp.split(',')[1]}, true>(const Code, const Tables, const SweepArgs);",
-        "retry": f"template __global__ void pb::dl_retry_kernel<{tp.split(',')[0]}, {tp.split(',')[1]}>(const Code, const Tables, const SweepArgs);"}[kind]
+        "sweep": f"template __global__ void pb::sweep_kernel<{tp}>(const Code, const Tables, const SweepArgs);",
+        "sweeptrace": f"template __global__ void pb::sweep_kernel<{tp}>(const Code, const Tables, const SweepArgs);",
+        "retry": f"template __global__ void pb::dl_retry_kernel<{tp}>(const Code, const Tables, const SweepArgs);"}[kind]
 d = Path(tempfile.mkdtemp())
 (d / "one.cu").write_text(f'#include "{ROOT}/polar_code_b200/csrc/polar_sweep.cuh"\nusing namespace pb;\n{inst}\n')
 r = subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-diag-suppress", "177",
-                    "-Xptxas", "-v", "-cubin", "-o", str(d / "one.cubin"), str(d / "one.cu")], capture_output=True, text=True)
+                    "-Xptxas", "-v", *[a for a in args if a.startswith("-D")], "-cubin", "-o", str(d / "one.cubin"), str(d / "one.cu")], capture_output=True, text=True)
 if r.returncode: raise SystemExit(r.stderr)
 print([l for l in r.stderr.splitlines() if "registers" in l or "spill" in l])
 sass = subprocess.run(["nvdisasm", "-g", "-c", str(d / "one.cubin")], capture_output=True, text=True).stdout
