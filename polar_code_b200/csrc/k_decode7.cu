@@ -11,3 +11,13 @@ const void* pb_decode_kernel_7(int MP, bool forced, bool metric) {
         default: return forced ? (const void*)decode_kernel<8, 7, true, true> : (const void*)decode_kernel<8, 7, false, true>;
     }
 }
+
+// trace-recording list decode (info_llrs of all M paths requested): FORCED kernels only, force may be null
+const void* pb_decode_kernel_7_trace(int MP) {
+    switch (MP) {
+        case 1: return (const void*)decode_kernel<1, 7, true, true, 0, true>;
+        case 2: return (const void*)decode_kernel<2, 7, true, true, 0, true>;
+        case 4: return (const void*)decode_kernel<4, 7, true, true, 0, true>;
+        default: return (const void*)decode_kernel<8, 7, true, true, 0, true>;
+    }
+}

@@ -11,3 +11,13 @@ const void* pb_decode_kernel_9(int MP, bool forced, bool metric) {
         default: return forced ? (const void*)decode_kernel<8, 9, true, true> : (const void*)decode_kernel<8, 9, false, true>;
     }
 }
+
+// trace-recording list decode (info_llrs of all M paths requested): FORCED kernels only, force may be null
+const void* pb_decode_kernel_9_trace(int MP) {
+    switch (MP) {
+        case 1: return (const void*)decode_kernel<1, 9, true, true, 0, true>;
+        case 2: return (const void*)decode_kernel<2, 9, true, true, 0, true>;
+        case 4: return (const void*)decode_kernel<4, 9, true, true, 0, true>;
+        default: return (const void*)decode_kernel<8, 9, true, true, 0, true>;
+    }
+}

@@ -251,9 +251,13 @@ extern "C" int pb200_create(pb200_engine** out, int device, int N, const int32_t
     return PB200_OK;
 }
 
+static void l2_release_window(int device);
+
 extern "C" void pb200_destroy(pb200_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
+    for (auto& kv : e->l2_window)                  // hand this engine's share of the L2 set-aside back
+        if (kv.second.first != nullptr && e->device >= 0 && e->device < 64) l2_release_window(e->device);
     cudaFree(e->d_info_pos); cudaFree(e->d_info_mask); cudaFree(e->d_crc_tab); cudaFree(e->d_rm_src); cudaFree(e->d_rm_cnt); cudaFree(e->d_tx_src);
     for (auto& kv : e->enc_tabs) cudaFree(kv.second);
     cudaFree(e->d_llr_store); cudaFree(e->d_abs_store); cudaFree(e->d_rm_dst); cudaFree(e->d_beta64);
@@ -335,7 +339,8 @@ extern "C" int pb200_set_rate_matching(pb200_engine* e, int E) {
 // ---------------------------------------------------------------------------------------------------
 // Kernel selection
 // ---------------------------------------------------------------------------------------------------
-static const void* pick_decode(int n, int MP, bool forced, bool metric) {
+static const void* pick_decode(int n, int MP, bool forced, bool metric, bool trace = false) {
+    if (trace) return n == 7 ? pb_decode_kernel_7s_trace(MP) : n < 7 ? pb_decode_kernel_7_trace(MP) : pb_decode_kernel_9_trace(MP);
     if (n == 7) return pb_decode_kernel_7s(MP, forced, metric);      // the headline geometry N = 128: static code length
     return n < 7 ? pb_decode_kernel_7(MP, forced, metric) : pb_decode_kernel_9(MP, forced, metric);
 }
@@ -373,14 +378,25 @@ static int ensure_scratch(pb200_engine* e, cudaStream_t st, size_t warps, int MP
 // while everything else the stream touches -- the LLR rows in, the decisions out -- keeps the normal policy:
 // an access-policy window over the scratch with the persisting property, backed by an L2 set-aside.  Best effort
 // (older drivers / MIG slices without the feature just run without it).  Only the list kernels (MP >= 2) ask for it;
-// a thread-per-frame launch (SC / M = 1) clears the window of ITS stream only.
-// The set-aside (cudaLimitPersistingL2CacheSize) is DEVICE-wide state: it is taken once per device by the first engine
-// that needs it, recorded in process-global state and never changed from a launch path again -- other engines, streams
-// and libraries in the process keep whatever residency they arranged.  PB200_L2_PIN=0 switches the feature off;
-// PB200_L2_SETASIDE_MB caps the set-aside (default: all the device allows) for processes that share the GPU's L2.
-struct L2DeviceState { bool probed = false, limit_set = false; int window_max = 0, persist_max = 0; };
+// a thread-per-frame launch (SC / M = 1) clears the window of ITS stream.
+// The set-aside (cudaLimitPersistingL2CacheSize) is DEVICE-wide state, so it is managed in process-global, reference-
+// counted state per device: it is taken when the first (engine, stream) window is set and given back -- persisting lines
+// demoted -- when the last one is cleared (by a thread-per-frame launch on that stream or by pb200_destroy).  While any
+// engine's list kernels hold a window nobody's launch path changes the limit.  Giving it back matters: an unused 79 MB
+// set-aside leaves SC / M = 1 only 47 MB of L2 (measured: 0.69e9 instead of 1.6e9 frames/s).
+// PB200_L2_PIN=0 switches the feature off; PB200_L2_SETASIDE_MB caps the set-aside (default: all the device allows).
+struct L2DeviceState { bool probed = false; int window_max = 0, persist_max = 0, active_windows = 0; };
 static L2DeviceState g_l2[64];
 static std::mutex g_l2_mutex;
+
+static void l2_release_window(int device) {            // one (engine, stream) window less; the last one frees the set-aside
+    std::lock_guard<std::mutex> lock(g_l2_mutex);
+    L2DeviceState& g = g_l2[device];
+    if (g.active_windows > 0 && --g.active_windows == 0) {
+        if (cudaCtxResetPersistingL2Cache() != cudaSuccess) cudaGetLastError();
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0) != cudaSuccess) cudaGetLastError();
+    }
+}
 
 static void pin_scratch_in_l2(pb200_engine* e, cudaStream_t st, unsigned char* scratch, size_t bytes, bool enable) {
     if (e->l2_window_max == -1) {
@@ -399,8 +415,10 @@ static void pin_scratch_in_l2(pb200_engine* e, cudaStream_t st, unsigned char* s
         v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
         if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
         it->second = {nullptr, 0};
+        l2_release_window(e->device);
         return;
     }
+    auto& cur = e->l2_window[st];
     L2DeviceState ds;
     {
         std::lock_guard<std::mutex> lock(g_l2_mutex);
@@ -414,14 +432,13 @@ static void pin_scratch_in_l2(pb200_engine* e, cudaStream_t st, unsigned char* s
             }
             g.probed = true;
         }
-        if (g.window_max > 0 && g.persist_max > 0 && !g.limit_set) {
-            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)g.persist_max) != cudaSuccess) cudaGetLastError();
-            g.limit_set = true;
+        if (g.window_max > 0 && g.persist_max > 0 && cur.first == nullptr) {
+            if (g.active_windows++ == 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)g.persist_max) != cudaSuccess)
+                cudaGetLastError();
         }
         ds = g;
     }
     if (ds.window_max <= 0 || ds.persist_max <= 0) return;
-    auto& cur = e->l2_window[st];
     if (cur.first == scratch && cur.second == bytes) return;
     cudaStreamAttrValue v{};
     v.accessPolicyWindow.base_ptr = scratch;
@@ -479,9 +496,10 @@ static int choose_cfg(pb200_engine* e, const void* fn, int MP, int key_kind, siz
 static int launch_decode(pb200_engine* e, int M, bool metric, const DecodeArgs& a, cudaStream_t st) {
     const int MP = metric ? round_mp(M) : 1;
     const bool forced = a.force != nullptr;
-    const void* fn = pick_decode(e->code.n, MP, forced, metric);
+    const bool trace = metric && a.info_llrs != nullptr;       // info_llrs of all paths: read off the leaf-LLR trace
+    const void* fn = pick_decode(e->code.n, MP, forced, metric, trace);
     KernelCfg kc;
-    int rc = choose_cfg(e, fn, MP, (forced ? 1 : 0) | (metric ? 2 : 0), warp_bytes(MP, e->code.N, 0), &kc);
+    int rc = choose_cfg(e, fn, MP, trace ? 8 : ((forced ? 1 : 0) | (metric ? 2 : 0)), warp_bytes(MP, e->code.N, 0, false, trace ? e->code.K : 0), &kc);
     if (rc) return rc;
     Code code = e->code;
     code.M = metric ? M : 1;
@@ -492,7 +510,8 @@ static int launch_decode(pb200_engine* e, int M, bool metric, const DecodeArgs& 
     DecodeArgs aa = a;
     rc = ensure_scratch(e, st, (size_t)grid * kc.wpc, MP, &aa.gscratch);
     if (rc) return rc;
-    pin_scratch_in_l2(e, st, aa.gscratch, (size_t)grid * kc.wpc * warp_gbytes(MP, e->code.N, 0), MP >= 2);
+    static const bool pin_m1 = [] { const char* v = getenv("PB200_L2_PIN_M1"); return v && v[0] == '1'; }();
+    pin_scratch_in_l2(e, st, aa.gscratch, (size_t)grid * kc.wpc * warp_gbytes(MP, e->code.N, 0), MP >= 2 || pin_m1);
     void* args[3] = {(void*)&code, (void*)&e->tb, (void*)&aa};
     CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(kc.wpc * 32), args, kc.smem, st));
     return PB200_OK;

@@ -284,8 +284,21 @@ struct ListDecoder {
                 else set_bit_odd<true>(code, p, phi, bit);
             } else set_bit_odd<R == 1>(code, p, phi, bit);
         };
-        if constexpr (!FORCED && !TRACE && MP == 1) {
-            // thread-per-frame kernels (no rank/clone code): fully static blocks of four phases (measured +7 % over pairs)
+        // Loop forms.  4 = fully static blocks of four phases (even/odd split, the height-1 recompute of phases 2 mod 4 and
+        // the one-level partial-sum update of phases 1 mod 4 need no dispatch; four copies of the phase body),
+        // 2 = phase pairs with one warp-uniform pair-kind branch (two copies), 1 = compact loop (one copy).
+        // Measured on B200 (round 2, static-N kernels, 1 Mi+ frames): plain list kernels 4 > 2 by 3-4 % (M = 2, 4, 8 and the
+        // fused sweep; in round 1 the larger body of that build stalled on instruction fetch and pairs won); forced /
+        // trace-recording kernels 2 > 1 by 5-7 % on the DL-SCL legs.
+#ifndef PB_LIST_FORM
+#define PB_LIST_FORM 4
+#endif
+#ifndef PB_TRACE_FORM
+#define PB_TRACE_FORM 2
+#endif
+        constexpr int FORM = (!FORCED && !TRACE) ? (MP == 1 ? 4 : PB_LIST_FORM) : PB_TRACE_FORM;
+        if constexpr (FORM == 4) {
+#pragma unroll 1
             for (int phi0 = 0; phi0 < N; phi0 += 4) {
                 phase(phi0, std::integral_constant<int, 0>{}, 0);
                 phase(phi0 + 1, std::integral_constant<int, 1>{}, 0);
@@ -294,12 +307,7 @@ struct ListDecoder {
                     phase(phi0 + 3, std::integral_constant<int, 3>{}, 1);
                 }
             }
-        } else if constexpr (!FORCED && !TRACE) {
-            // list kernels: phase pairs.  Even/odd is static; which of the two pair kinds it is (phi = 0/1 or 2/3 mod 4)
-            // is one uniform branch around the statically specialised recompute / partial-sum update -- two copies of
-            // the rank/clone code instead of four.  Measured on M = 4: 2 915 instead of 2 786 warp-instructions per
-            // frame, but no_instruction stalls 0.31 instead of 1.16 per issue and 78 % instead of 73 % issue slots busy
-            // (+3.6 % frames/s).
+        } else if constexpr (FORM == 2) {
 #pragma unroll 1
             for (int phi0 = 0; phi0 < N; phi0 += 2) {
                 const int half = (phi0 >> 1) & 1;
@@ -368,35 +376,6 @@ struct ListDecoder {
                 const int j = j0 + i * MP;
                 if (j <= jtop) sink(j, v[i]);
             }
-        }
-    }
-
-    // SC pass along the known bits `u` (own slot only), reporting the leaf LLR of every information phase:
-    // the values a path saw during list decoding (scl.py:159,167 info_llrs), recomputed instead of copied.
-    template <typename Sink>
-    static __device__ __forceinline__ void replay(const Code& code, const uint32_t* __restrict__ imask, const WM& wm, int lane,
-                                                  bool active, const float* chanf, const uint32_t (&u)[XW], Sink&& sink) {
-        PathT q;
-        init(q, lane, true);
-        q.alive = active;
-        q.P = (lane & (MP - 1)) * 0x11111111u;
-        int j = 0;
-        uint32_t cur_info = 0, cur_u = 0;
-        float a = 0.f, b = 0.f;
-        for (int phi = 0; phi < code.N; ++phi) {
-            if ((phi & 31) == 0) {
-                cur_info = __ldg(imask + (phi >> 5));
-#pragma unroll
-                for (int k = 0; k < XW; ++k) if (k == (phi >> 5)) cur_u = u[k];
-            }
-            const bool odd = phi & 1;
-            float L;
-            if (!odd) { pair_llr(code, wm, q, phi, lane, chanf, a, b); L = f_op(a, b); }
-            else L = g_op_packed(a, b, q.bw[0], 0);
-            if ((cur_info >> (phi & 31)) & 1u) { if (active) sink(j, L); ++j; }
-            const uint32_t bit = (cur_u >> (phi & 31)) & 1u;
-            if (!odd) q.bw[0] = (q.bw[0] & ~1u) | bit;
-            else set_bit_odd(code, q, phi, bit);
         }
     }
 };

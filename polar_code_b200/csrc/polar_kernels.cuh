@@ -105,7 +105,7 @@ __device__ __forceinline__ void load_force(const Code& code, const int8_t* force
         if (w * 32 < code.N) {
             for (int b = 0; b < 32 && w * 32 + b < code.N; ++b) {
                 if ((code.info_mask[w] >> b) & 1u) {
-                    if (valid) {
+                    if (valid && force != nullptr) {
                         const int v = force[frame * (int64_t)code.K + j];
                         if (v == 0 || v == 1) { fmask[w] |= 1u << b; fval[w] |= (uint32_t)v << b; }
                         else if (v != -1) flags |= 4u;
@@ -122,7 +122,10 @@ __device__ __forceinline__ void load_force(const Code& code, const int8_t* force
 #endif
 // N <= 128: compiled for 1024 threads per CTA, i.e. 64 registers -> 32 resident warps per SM (no spills for the plain
 // kernels, a few dozen bytes for the forced ones); N = 256 / 512 keep 16 partial-sum words per path and get 128 registers.
-template <int MP, int LOGMAX, bool FORCED, bool METRIC, int NS = 0, int HS = DefaultHS<MP>::value>
+// TRACE (instantiated for FORCED kernels only; a.force may then be null): the list decode records the leaf-LLR trace and
+// info_llrs[B,M,K] (scl.py:159,167,203-209) of all M paths is read off it -- K shared-memory reads and K/MP loads per
+// path instead of one SC replay per path.
+template <int MP, int LOGMAX, bool FORCED, bool METRIC, int NS = 0, bool TRACE = false, int HS = DefaultHS<MP>::value>
 __global__ void __launch_bounds__(LOGMAX <= 7 ? (MP > 1 ? PB_LIST_THREADS : 1024) : 512) decode_kernel(const Code code_, const Tables tb, const DecodeArgs a) {
     const Code code = with_static_n<NS>(code_);
     using Dec = ListDecoder<MP, LOGMAX, FORCED, METRIC, HS>;
@@ -133,7 +136,8 @@ __global__ void __launch_bounds__(LOGMAX <= 7 ? (MP > 1 ? PB_LIST_THREADS : 1024
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpc = blockDim.x >> 5;
     WM wm;
-    wm.carve(smem + (size_t)warp * WM::bytes(code.N), WM::warp_scratch(a.gscratch, code.N), code.N);
+    wm.carve(smem + (size_t)warp * WM::bytes(code.N, 0, TRACE ? code.K : 0), WM::warp_scratch(a.gscratch, code.N), code.N, 0,
+             TRACE ? WM::warp_trace(a.gscratch, code.N, code.K) : nullptr, TRACE ? code.K : 0);
     const int K = code.K, M = code.M;
     const int xwn = code.N >= 32 ? code.N / 32 : 1;
     const int64_t ngroups = (a.B + FPW - 1) / FPW;
@@ -152,7 +156,7 @@ __global__ void __launch_bounds__(LOGMAX <= 7 ? (MP > 1 ? PB_LIST_THREADS : 1024
         if constexpr (FORCED) load_force<XW>(code, a.force, frame, valid, fmask, fval, flags);
         PathT p;
         Dec::init(p, lane, valid);
-        Dec::run(code, tb.info_mask, wm, p, lane, chanf, fmask, fval, flags);
+        Dec::template run<TRACE>(code, tb.info_mask, wm, p, lane, chanf, fmask, fval, flags);
 
         // u-hat = x-hat * F^{(x)n}
         uint32_t u[XW];
@@ -171,10 +175,19 @@ __global__ void __launch_bounds__(LOGMAX <= 7 ? (MP > 1 ? PB_LIST_THREADS : 1024
 #pragma unroll
         for (int o = 1; o < MP; o <<= 1) fl |= __shfl_xor_sync(kFull, fl, o);
 
-        if (a.info_llrs != nullptr) {
-            float* dst = a.info_llrs + ((frame * M + p.r) * (int64_t)K);
-            Dec::replay(code, tb.info_mask, wm, lane, p.alive, chanf, u, [&](int j, float L) { dst[j] = L; });
-            __syncwarp();
+        if constexpr (TRACE) {
+            if (a.info_llrs != nullptr) {
+                // one lineage walk per path of the group: candidate p.r of the frame = the path that ended in slot s
+#pragma unroll
+                for (int s = 0; s < MP; ++s) {
+                    const int end_lane = (lane & ~(MP - 1)) + s;
+                    const bool al = __shfl_sync(kFull, (int)p.alive, end_lane) != 0;
+                    const uint32_t rs = __shfl_sync(kFull, p.r, end_lane);
+                    float* dst = a.info_llrs + ((frame * M + rs) * (int64_t)K);
+                    Dec::trace_walk(code, wm, lane, end_lane, [&](int j, float L) { if (al && valid) dst[j] = L; });
+                }
+                __syncwarp();
+            }
         }
         // stash u-hat words in the (now dead) tree area of the own slot for dynamic bit addressing
         float* stash = wm.scr + lane;

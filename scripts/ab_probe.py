@@ -16,14 +16,15 @@ B = 1 << 21
 
 
 def timeit(fn, reps=5):
-    fn(); fn()
+    """median of `reps` individually timed calls after three warm-up calls"""
+    fn(); fn(); fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    ts = []
     for _ in range(reps):
-        fn()
-    e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
 
 
 parts = [eng.channel(noise_var=nv(s), n_frames=B // 6 + 1, frame_begin=i * B, seed=2026, stream_id=i, k_payload=40)[1] for i, s in enumerate([4.0, 4.5, 5.0, 5.5, 6.0, 6.5])]
@@ -35,11 +36,11 @@ for M in (4, 8, 2, 1):
 c = torch.zeros(16, dtype=torch.int64, device="cuda")
 ms = timeit(lambda: eng.sweep(c, M=4, noise_var=nv(5.0), n_frames=B, seed=1, stream_id=2, k_payload=40), 3)
 res["sweep_M4_5dB"] = B / ms * 1e3
-for M, snr in ((4, 4.0), (4, 5.0), (8, 5.0)):
+for M, snr in ((4, 4.0), (4, 5.0), (8, 5.0), (8, 4.0)):
     beta = torch.as_tensor(g[f"beta_M{M}"], device="cuda")
-    ms = timeit(lambda: eng.sweep(c, M=M, noise_var=nv(snr), n_frames=B, seed=1, stream_id=3, k_payload=40, retries=8, beta=beta), 3)
+    ms = timeit(lambda: eng.sweep(c, M=M, noise_var=nv(snr), n_frames=B, seed=1, stream_id=3, k_payload=40, retries=8, beta=beta), 7)
     res[f"dl_M{M}_r8_beta_{snr}dB"] = B / ms * 1e3
-ms = timeit(lambda: eng.sweep(c, M=4, noise_var=nv(4.0), n_frames=B, seed=1, stream_id=3, k_payload=40, retries=8), 3)
+ms = timeit(lambda: eng.sweep(c, M=4, noise_var=nv(4.0), n_frames=B, seed=1, stream_id=3, k_payload=40, retries=8), 7)
 res["dl_M4_r8_nobeta_4.0dB"] = B / ms * 1e3
 print(tag, " ".join(f"{k}={v:.4g}" for k, v in res.items()), flush=True)
 
