@@ -494,6 +494,22 @@ def extra_legs(eng, llr, msg, dev, B) -> dict:
     ms = time_it(lambda: nr.sweep(counters, M=M, noise_var=mc.ber_noise_var(3.0, 64, 256), n_frames=Bx, seed=1, stream_id=4, k_payload=64,
                                   frame_error_mode=1, bit_error_span=64))
     out["fused_nr_E256_K88_M4_frames_per_s"] = Bx / (ms * 1e-3)
+    # OPTIONAL binary16 ingest of the host-buffer path (pb200_scl_decode_host_f16: half the host->device bytes, rows widened
+    # exactly on load).  Not the headline: quantising LLRs to binary16 is the caller's decision (include/polar_b200.h).
+    Bh = min(B, 1 << 20)
+    h16 = torch.empty((Bh, N), dtype=torch.float16, pin_memory=True)
+    h16.copy_(llr[:Bh].half())
+    h_bits = torch.empty((Bh, K), dtype=torch.uint8, pin_memory=True)
+    h_ok = torch.empty((Bh,), dtype=torch.uint8, pin_memory=True)
+    h_fl = torch.empty((Bh,), dtype=torch.int32, pin_memory=True)
+    for _ in range(2):
+        eng.scl_decode_host(h16, M, h_bits, h_ok, h_fl)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        eng.scl_decode_host(h16, M, h_bits, h_ok, h_fl)
+    torch.cuda.synchronize()
+    out["e2e_f16_ingest_frames_per_s"] = 5 * Bh / (time.perf_counter() - t0)
     return out
 
 

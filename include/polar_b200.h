@@ -119,6 +119,12 @@ int pb200_choose_flip_index_batch(const float *d_abs_l0, const float *d_beta, in
  * flags[B] are copied back.  Synchronous. */
 int pb200_scl_decode_host(pb200_engine *e, const float *h_llr, int64_t B, int in_len, int M, uint8_t *h_best_bits,
                           uint8_t *h_crc_ok, uint32_t *h_flags);
+/* The same with the LLR rows given as IEEE binary16 (OPTIONAL ingest format: half the host->device bytes, which is what
+ * bounds the host-buffer path).  Rows are widened to fp32 on load -- exactly -- so the result equals
+ * pb200_scl_decode_host on the same values as fp32; quantising float LLRs to binary16 is the CALLER's decision and is
+ * outside the parity contract of scl.py:108-209. */
+int pb200_scl_decode_host_f16(pb200_engine *e, const uint16_t *h_llr_f16, int64_t B, int in_len, int M,
+                              uint8_t *h_best_bits, uint8_t *h_crc_ok, uint32_t *h_flags);
 
 /* ---- Monte-Carlo sweeps (channel + decode + counters fused on the GPU) -------------------------
  * eval/run_fer_sweep.py:60-121 and eval/run_ber_sweep.py:112-181.  Frames are numbered globally;

@@ -62,6 +62,7 @@ SYMBOLS = {
     "pb200_dlscl_decode_batch": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(DlOut), _vp]),
     "pb200_choose_flip_index_batch": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, _vp]),
     "pb200_scl_decode_host": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "pb200_scl_decode_host_f16": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp]),
     "pb200_sweep": (C.c_int, [_vp, C.POINTER(SweepCfg), _vp, _vp, _vp, _vp, _vp]),
     "pb200_channel_batch": (C.c_int, [_vp, C.POINTER(SweepCfg), _vp, _vp, _vp]),
     "pb200_kernel_info": (C.c_int, [_vp, C.c_int] + [C.POINTER(C.c_int)] * 4),

@@ -1,4 +1,5 @@
 // polar_abi.cu -- C-ABI of libpolar_b200.so (see include/polar_b200.h) and kernel dispatch.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
@@ -124,6 +125,7 @@ struct pb200_engine {
     uint8_t* d_stage_bits[3] = {nullptr, nullptr, nullptr};
     uint8_t* d_stage_ok[3] = {nullptr, nullptr, nullptr};
     uint32_t* d_stage_flags[3] = {nullptr, nullptr, nullptr};
+    uint16_t* d_stage_half[3] = {nullptr, nullptr, nullptr};     // binary16 ingest: rows land here and are widened into d_stage_llr
     int64_t stage_frames = 0;
     int stage_len = 0;
     // NR + DL-SCL state
@@ -264,7 +266,7 @@ extern "C" void pb200_destroy(pb200_engine* e) {
     for (auto& kv : e->scratch) cudaFree(kv.second.first); cudaFree(e->d_q[0]); cudaFree(e->d_q[1]); cudaFree(e->d_q_counts);
     for (int i = 0; i < 3; ++i) {
         if (e->hs[i]) cudaStreamDestroy(e->hs[i]);
-        cudaFree(e->d_stage_llr[i]); cudaFree(e->d_stage_bits[i]); cudaFree(e->d_stage_ok[i]); cudaFree(e->d_stage_flags[i]);
+        cudaFree(e->d_stage_llr[i]); cudaFree(e->d_stage_bits[i]); cudaFree(e->d_stage_ok[i]); cudaFree(e->d_stage_flags[i]); cudaFree(e->d_stage_half[i]);
     }
     delete e;
 }
@@ -609,23 +611,37 @@ extern "C" int pb200_scl_decode_batch(pb200_engine* e, const float* llr, int64_t
     return launch_decode(e, M, true, a, (cudaStream_t)stream);
 }
 
+// binary16 rows -> fp32 rows (exact).  The host-buffer path is bound by the host->device copy, so the widening pass over
+// the staged chunk (0.75 KB of HBM traffic per frame) is free and the decode kernels keep a single input format.
+static __global__ void widen_rows_kernel(const __half* __restrict__ in, float* __restrict__ out, size_t n) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i + 1 < n) {
+        const float2 v = __half22float2(*reinterpret_cast<const __half2*>(in + i));
+        *reinterpret_cast<float2*>(out + i) = v;
+    } else if (i < n) out[i] = __half2float(in[i]);
+}
+
 // Host buffers in, host buffers out: chunked, triple-buffered copy/compute overlap on internal streams.
-extern "C" int pb200_scl_decode_host(pb200_engine* e, const float* h_llr, int64_t B, int in_len, int M, uint8_t* h_bits,
-                                     uint8_t* h_ok, uint32_t* h_flags) {
-    int rc = check_decode_args(e, h_llr, B, in_len, M);
+// elem = bytes per LLR (4: fp32 rows, 2: binary16 rows).
+static int decode_host_common(pb200_engine* e, const void* h_llr, int elem, int64_t B, int in_len, int M, uint8_t* h_bits,
+                              uint8_t* h_ok, uint32_t* h_flags) {
+    int rc = check_decode_args(e, reinterpret_cast<const float*>(h_llr), B, in_len, M);
     if (rc) return rc;
     if (B == 0) return PB200_OK;
     CUDA_TRY(cudaSetDevice(e->device));
     const int K = e->code.K;
-    // 2^16 frames (32 MiB of LLRs) per chunk: the pipeline's fill (first copy-in) and drain (last decode + copy-out)
+    // 2^16 frames (32 MiB of fp32 LLRs) per chunk: the pipeline's fill (first copy-in) and drain (last decode + copy-out)
     // are not overlapped, so small chunks keep them short; a chunk still fills the GPU (8 192 warps of work)
     const int64_t chunk = std::min<int64_t>(B, 1 << 16);
     if (e->stage_frames < chunk || e->stage_len != in_len) {
         for (int i = 0; i < 3; ++i) {
             cudaFree(e->d_stage_llr[i]); cudaFree(e->d_stage_bits[i]); cudaFree(e->d_stage_ok[i]); cudaFree(e->d_stage_flags[i]);
+            cudaFree(e->d_stage_half[i]);
             e->d_stage_llr[i] = nullptr; e->d_stage_bits[i] = nullptr; e->d_stage_ok[i] = nullptr; e->d_stage_flags[i] = nullptr;
+            e->d_stage_half[i] = nullptr;
             if (!e->hs[i]) CUDA_TRY(cudaStreamCreateWithFlags(&e->hs[i], cudaStreamNonBlocking));
             CUDA_TRY(cudaMalloc((void**)&e->d_stage_llr[i], (size_t)chunk * in_len * 4));
+            CUDA_TRY(cudaMalloc((void**)&e->d_stage_half[i], (size_t)chunk * in_len * 2));
             CUDA_TRY(cudaMalloc((void**)&e->d_stage_bits[i], (size_t)chunk * K));
             CUDA_TRY(cudaMalloc((void**)&e->d_stage_ok[i], (size_t)chunk));
             CUDA_TRY(cudaMalloc((void**)&e->d_stage_flags[i], (size_t)chunk * 4));
@@ -638,7 +654,14 @@ extern "C" int pb200_scl_decode_host(pb200_engine* e, const float* h_llr, int64_
     while (done < B) {
         const int64_t nb = std::min<int64_t>(chunk, B - done);
         cudaStream_t st = e->hs[slot];
-        CUDA_TRY(cudaMemcpyAsync(e->d_stage_llr[slot], h_llr + done * in_len, (size_t)nb * in_len * 4, cudaMemcpyHostToDevice, st));
+        void* land = elem == 4 ? (void*)e->d_stage_llr[slot] : (void*)e->d_stage_half[slot];
+        CUDA_TRY(cudaMemcpyAsync(land, reinterpret_cast<const unsigned char*>(h_llr) + (size_t)done * in_len * elem,
+                                 (size_t)nb * in_len * elem, cudaMemcpyHostToDevice, st));
+        if (elem == 2) {
+            const size_t n = (size_t)nb * in_len;
+            widen_rows_kernel<<<(unsigned)((n / 2 + 256) / 256), 256, 0, st>>>(reinterpret_cast<const __half*>(e->d_stage_half[slot]), e->d_stage_llr[slot], n);
+            CUDA_TRY(cudaGetLastError());
+        }
         DecodeArgs a{};
         a.llr = e->d_stage_llr[slot]; a.B = nb; a.in_len = in_len;
         a.best_bits = e->d_stage_bits[slot]; a.crc_ok = e->d_stage_ok[slot]; a.flags = e->d_stage_flags[slot];
@@ -652,6 +675,16 @@ extern "C" int pb200_scl_decode_host(pb200_engine* e, const float* h_llr, int64_
     }
     for (int i = 0; i < 3; ++i) CUDA_TRY(cudaStreamSynchronize(e->hs[i]));
     return PB200_OK;
+}
+
+extern "C" int pb200_scl_decode_host(pb200_engine* e, const float* h_llr, int64_t B, int in_len, int M, uint8_t* h_bits,
+                                     uint8_t* h_ok, uint32_t* h_flags) {
+    return decode_host_common(e, h_llr, 4, B, in_len, M, h_bits, h_ok, h_flags);
+}
+
+extern "C" int pb200_scl_decode_host_f16(pb200_engine* e, const uint16_t* h_llr_f16, int64_t B, int in_len, int M, uint8_t* h_bits,
+                                         uint8_t* h_ok, uint32_t* h_flags) {
+    return decode_host_common(e, h_llr_f16, 2, B, in_len, M, h_bits, h_ok, h_flags);
 }
 
 #include "polar_abi_sweep.inl"

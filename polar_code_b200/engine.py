@@ -188,9 +188,13 @@ class PolarEngine:
 
     def scl_decode_host(self, llr_host: torch.Tensor, M: int, best_bits: torch.Tensor, crc_ok: torch.Tensor,
                         flags: torch.Tensor) -> None:
-        """Host buffers in / out (pinned for full speed); chunked copy/compute overlap inside the library."""
+        """Host buffers in / out (pinned for full speed); chunked copy/compute overlap inside the library.
+        `llr_host` is float32 [B, in_len], or float16 (optional ingest format: rows are widened exactly on load)."""
         B = llr_host.shape[0]
-        L.check(self.lib.pb200_scl_decode_host(self._h, C.c_void_p(llr_host.data_ptr()), B, llr_host.shape[1], int(M),
+        if llr_host.dtype not in (torch.float32, torch.float16) or llr_host.is_cuda or not llr_host.is_contiguous():
+            raise ValueError("llr_host must be a contiguous float32 / float16 host tensor")
+        fn = self.lib.pb200_scl_decode_host if llr_host.dtype == torch.float32 else self.lib.pb200_scl_decode_host_f16
+        L.check(fn(self._h, C.c_void_p(llr_host.data_ptr()), B, llr_host.shape[1], int(M),
                                                C.c_void_p(best_bits.data_ptr()), C.c_void_p(crc_ok.data_ptr()),
                                                C.c_void_p(flags.data_ptr())))
 

@@ -198,6 +198,25 @@ def test_host_buffer_path_matches_device_path(eng):
     assert torch.equal(h_fl, ref["flags"].cpu())
 
 
+@pytest.mark.parametrize("M", [4, 1])
+def test_host_buffer_f16_ingest_is_exact_widening(eng, M):
+    """pb200_scl_decode_host_f16: binary16 rows are widened to fp32 on load -- the result equals the fp32 host path on
+    the widened values bit for bit (ragged batch, > 2 chunks).  Quantising is the caller's choice, outside scl.py's contract."""
+    n = (1 << 17) + 4321
+    _, llr = eng.channel(noise_var=_nv(4.5), n_frames=n, seed=9, stream_id=2, k_payload=40)
+    h16 = torch.empty((n, 128), dtype=torch.float16, pin_memory=True)
+    h16.copy_(llr.half())
+    ref = eng.scl_decode(h16.to("cuda").float(), M, want=("best_bits", "crc_ok", "flags"))
+    h_bits = torch.empty((n, 64), dtype=torch.uint8, pin_memory=True)
+    h_ok = torch.empty((n,), dtype=torch.uint8, pin_memory=True)
+    h_fl = torch.empty((n,), dtype=torch.int32, pin_memory=True)
+    eng.scl_decode_host(h16, M, h_bits, h_ok, h_fl)
+    assert torch.equal(h_bits, ref["best_bits"].cpu()) and torch.equal(h_ok, ref["crc_ok"].cpu())
+    assert torch.equal(h_fl, ref["flags"].cpu())
+    with pytest.raises(ValueError):
+        eng.scl_decode_host(h16.double(), M, h_bits, h_ok, h_fl)
+
+
 @pytest.mark.parametrize("M,snr", [(4, 4.5), (1, 5.0), (8, 4.0)])
 def test_fer_matches_oracle_on_reference_channel(eng, g128, M, snr):
     """FER / BER of the GPU sweep (Philox channel, 1e7 frames) against the float64 oracle fed by the reference's own
