@@ -165,6 +165,10 @@ int pb200_sweep(pb200_engine *e, const pb200_sweep_cfg *cfg, const float *d_beta
  * stream as pb200_sweep: msg[B,K] u8 (NULL ok), llr[B,E or N] f32. */
 int pb200_channel_batch(pb200_engine *e, const pb200_sweep_cfg *cfg, uint8_t *d_msg, float *d_llr, void *stream);
 
+/* Tuning aid: scheduler statistics of the engine's last binned DL-SCL retry launch (out8: waits on empty rings, lost
+ * claims, batches, frame decodes, sum of the batches' start phases, batches that mixed rings, 0, 0).  Synchronises. */
+int pb200_debug_bin_stats(pb200_engine *e, unsigned int *out8);
+
 /* Introspection for benchmarks: resident warps per SM, frames per warp, dynamic smem per CTA of the
  * decode kernel that (M, forced) selects. */
 int pb200_kernel_info(pb200_engine *e, int M, int *warps_per_cta, int *ctas_per_sm, int *smem_bytes, int *regs);

@@ -65,6 +65,7 @@ SYMBOLS = {
     "pb200_scl_decode_host_f16": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp]),
     "pb200_sweep": (C.c_int, [_vp, C.POINTER(SweepCfg), _vp, _vp, _vp, _vp, _vp]),
     "pb200_channel_batch": (C.c_int, [_vp, C.POINTER(SweepCfg), _vp, _vp, _vp]),
+    "pb200_debug_bin_stats": (C.c_int, [_vp, _vp]),
     "pb200_kernel_info": (C.c_int, [_vp, C.c_int] + [C.POINTER(C.c_int)] * 4),
     "pb200_ldpc_build_h": (C.c_int, [C.c_int, C.c_int, _vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pb200_ldpc_create": (C.c_int, [C.POINTER(_vp), C.c_int, _vp, C.c_int, C.c_int]),

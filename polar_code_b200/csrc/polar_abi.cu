@@ -138,6 +138,11 @@ struct pb200_engine {
     size_t llr_store_bytes = 0;
     float* d_abs_store = nullptr;         // |L0| rows of frames in the DL-SCL retry queue
     size_t abs_store_bytes = 0;
+    int* d_bin_ring = nullptr;            // dl_bin_kernel: one ring of queue-entry indices per flip index
+    size_t bin_ring_bytes = 0;
+    unsigned int* d_bin_ctrl = nullptr;   // cursor, finished count, ring heads and tails
+    int bin_ctrl_n = 0;
+    int dl_binned = -1;                   // -1: not read yet (PB200_DL_BINNED, default 1)
     double* d_beta64 = nullptr;           // the caller's beta widened to fp64 for the current call [K,K]
     // per-warp global scratch of the decode kernels, one buffer per stream: kernels of one engine that are
     // enqueued on different streams may overlap on the device and must not share tree rows
@@ -262,6 +267,7 @@ extern "C" void pb200_destroy(pb200_engine* e) {
         if (kv.second.first != nullptr && e->device >= 0 && e->device < 64) l2_release_window(e->device);
     cudaFree(e->d_info_pos); cudaFree(e->d_info_mask); cudaFree(e->d_crc_tab); cudaFree(e->d_rm_src); cudaFree(e->d_rm_cnt); cudaFree(e->d_tx_src);
     for (auto& kv : e->enc_tabs) cudaFree(kv.second);
+    cudaFree(e->d_bin_ring); cudaFree(e->d_bin_ctrl);
     cudaFree(e->d_llr_store); cudaFree(e->d_abs_store); cudaFree(e->d_rm_dst); cudaFree(e->d_beta64);
     for (auto& kv : e->scratch) cudaFree(kv.second.first); cudaFree(e->d_q[0]); cudaFree(e->d_q[1]); cudaFree(e->d_q_counts);
     for (int i = 0; i < 3; ++i) {

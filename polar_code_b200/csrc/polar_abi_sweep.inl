@@ -135,14 +135,31 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
     const bool trace = a.retries > 0;
     auto pick = [&](int kind) { return big ? pb_sweep_kernel_9(MP, kind) : code.n == 7 ? pb_sweep_kernel_7s(MP, kind) : pb_sweep_kernel_7(MP, kind); };
     const void* base = pick(trace ? 2 : 0);
-    const void* round = pick(1);
+    if (e->dl_binned < 0) { const char* env = getenv("PB200_DL_BINNED"); e->dl_binned = (env && env[0] == '0') ? 0 : 1; }
+    const bool binned = e->dl_binned != 0;
+    const void* round = pick(binned ? 3 : 1);
     KernelCfg kb, kr{};
     int rc = choose_cfg(e, base, MP, trace ? 6 : 4, warp_bytes(MP, code.N, 0, false, trace ? code.K : 0) + acc_bytes(MP), &kb);
     if (rc) return rc;
     int rgrid = 0;
     if (a.retries > 0) {
-        rc = choose_cfg(e, round, MP, 5, warp_bytes(MP, code.N, code.K, true, code.K) + acc_bytes(MP), &kr);
+        rc = choose_cfg(e, round, MP, binned ? 7 : 5, warp_bytes(MP, code.N, code.K, true, code.K) + acc_bytes(MP), &kr);
         if (rc) return rc;
+        if (binned) {
+            // The warps of a CTA run in lock step behind one scheduler warp, so the CTA's serial section (claim, ring slots,
+            // queue entries, LLR rows) idles all of them at once: split the resident warps over several CTAs per SM so that
+            // one CTA's serial section overlaps another's decode (PB200_DL_WPC overrides the warps per CTA).
+            int want_wpc = std::max(4, kr.wpc / 2);
+            if (const char* env = getenv("PB200_DL_WPC")) want_wpc = std::max(1, std::min(32, atoi(env)));
+            if (want_wpc < kr.wpc) {
+                const size_t wb = warp_bytes(MP, code.N, code.K, true, code.K) + acc_bytes(MP);
+                int blocks = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, round, want_wpc * 32, wb * want_wpc) == cudaSuccess &&
+                    blocks * want_wpc >= kr.wpc * kr.ctas_per_sm) {
+                    kr.wpc = want_wpc; kr.ctas_per_sm = blocks; kr.smem = (int)(wb * want_wpc);
+                } else cudaGetLastError();
+            }
+        }
         rgrid = std::max(1, e->sms * kr.ctas_per_sm);
     }
     const int fpw = 32 / MP;
@@ -215,6 +232,41 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
             q.q_in_count = e->d_q_counts;
             q.q_out = nullptr;
             q.q_out_count = e->d_q_counts + 1;
+            if (binned) {
+                // rings: a frame waits in the ring of the index it flips next.  The kernel keeps about inflight_target frames
+                // admitted (enough for every ring of a frequent index to hold full batches); the rings are sized beyond
+                // that plus everything the resident warps can hold, so they never wrap onto an unread slot.
+                const int K = code.K;
+                // Everything is admitted up front when the rings can hold it (256 MB of rings: 1 Mi frames in flight at
+                // K = 64): the frames then advance level by level and finish together, instead of a last generation that
+                // runs its eight sequential attempts on a draining GPU.
+                const size_t resident = (size_t)rgrid * kr.wpc * fpw;
+                size_t cap = 1024;
+                size_t cap_max = ((size_t)256 << 20) / ((size_t)K * sizeof(int));
+                if (const char* env = getenv("PB200_DL_RING_MB")) cap_max = ((size_t)std::max(1, atoi(env)) << 20) / ((size_t)K * sizeof(int));
+                while (cap < (size_t)nf && cap * 2 <= cap_max) cap *= 2;
+                const size_t slack = 2 * resident + (size_t)K * fpw;
+                while (cap < 2 * slack) cap *= 2;                              // (tiny budgets: at least the resident frames twice over)
+                q.inflight_target = (unsigned int)(cap >= (size_t)nf ? (size_t)nf : cap - slack);   // (a frame enters a ring at most once)
+                q.bin_cap = (unsigned int)cap;
+                const size_t ring_bytes = (size_t)K * cap * sizeof(int);
+                if (e->bin_ring_bytes < ring_bytes) {
+                    cudaFree(e->d_bin_ring);
+                    e->d_bin_ring = nullptr; e->bin_ring_bytes = 0;
+                    CUDA_TRY(cudaMalloc((void**)&e->d_bin_ring, ring_bytes));
+                    e->bin_ring_bytes = ring_bytes;
+                }
+                if (e->bin_ctrl_n < 96 + 32 * K) {
+                    cudaFree(e->d_bin_ctrl);
+                    e->d_bin_ctrl = nullptr; e->bin_ctrl_n = 0;
+                    CUDA_TRY(cudaMalloc((void**)&e->d_bin_ctrl, sizeof(unsigned int) * (96 + 32 * K)));
+                    e->bin_ctrl_n = 96 + 32 * K;
+                }
+                CUDA_TRY(cudaMemsetAsync(e->d_bin_ring, 0xff, ring_bytes, st));
+                CUDA_TRY(cudaMemsetAsync(e->d_bin_ctrl, 0, sizeof(unsigned int) * (96 + 32 * K), st));
+                q.bin_ring = e->d_bin_ring;
+                q.bin_ctrl = e->d_bin_ctrl;
+            }
             void* args[3] = {(void*)&code, (void*)&e->tb, (void*)&q};
             CUDA_TRY(cudaLaunchKernel(round, dim3(rgrid), dim3(kr.wpc * 32), args, kr.smem, st));
         }
@@ -268,6 +320,18 @@ extern "C" int pb200_dlscl_decode_batch(pb200_engine* e, const float* llr, int64
     a.n_attempts = out->n_attempts; a.tried = out->tried; a.flags = out->flags;
     a.R = std::max(retries, 1);
     return run_sweep(e, M, a, (cudaStream_t)stream);
+}
+
+// Scheduler statistics of the last dl_bin_kernel launch of this engine (tuning aid): waits on empty rings, lost claims,
+// batches, frame decodes, sum of the batches' start phases, batches mixing rings.  Synchronises the device.
+extern "C" int pb200_debug_bin_stats(pb200_engine* e, unsigned int* out8) {
+    if (!e || !out8) return fail(PB200_EINVAL, "NULL argument");
+    for (int i = 0; i < 8; ++i) out8[i] = 0;
+    if (!e->d_bin_ctrl) return PB200_OK;
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(out8, e->d_bin_ctrl + 64, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    return PB200_OK;
 }
 
 extern "C" int pb200_channel_batch(pb200_engine* e, const pb200_sweep_cfg* c, uint8_t* d_msg, float* d_llr, void* stream) {

@@ -144,7 +144,7 @@ struct WarpMem {
     float* chan;          // [N][FPW] staged channel LLRs, frame-interleaved (global scratch)
     float* scr;           // >= 3*max(N/32,1) lane-interleaved rows of scratch for the encoder / bit stash
     unsigned long long* xchg;  // [32][2] candidate keys for the rank exchange / small per-frame scratch (shared)
-    float* absl;          // [FPW][xk+1] DL-SCL only: |L0| of the reference path (flip.py:102) (shared)
+    float* absl;          // [FPW][absl_stride(xk)] DL-SCL only: |L0| of the reference path (flip.py:102) (shared)
     uint32_t* lin;        // [tk][4] trace mode only: ballot words (bit planes 0..2) of the slot each surviving path came
                           // from at info phase j (shared; written by lane 0)
     float* hist;          // [K][32] trace mode only: leaf LLR every slot saw at info phase j (global scratch)
@@ -159,7 +159,11 @@ struct WarpMem {
     __host__ __device__ static size_t lin_bytes(int tk) { return (tk && MP > 1) ? (size_t)tk * 16 : 0; }
     // The |L0| rows of the DL-SCL retry kernel are only live BETWEEN two list decodes (trace walk -> beta scoring), when
     // the tree rows are dead: they alias the shared tree area behind the stash rows whenever they fit there.
-    __host__ __device__ static size_t absl_bytes(int xk) { return xk ? (((size_t)FPW * (xk + 1) * 4 + 15) & ~(size_t)15) : 0; }
+    // Row stride of the |L0| rows: the FP64 tensor-core scoring (MP >= 4) reads element i0 + lane % 4 of frame lane / MP,
+    // conflict-free when consecutive frames are 4 banks apart (stride = 4 mod 32); the scalar scoring of MP < 4 reads the
+    // same element of all FPW frames (odd stride).
+    __host__ __device__ static int absl_stride(int xk) { return MP >= 4 ? (xk <= 4 ? 4 : ((xk - 4 + 31) / 32) * 32 + 4) : xk + 1; }
+    __host__ __device__ static size_t absl_bytes(int xk) { return xk ? (((size_t)FPW * absl_stride(xk) * 4 + 15) & ~(size_t)15) : 0; }
     // (the head of the tree area doubles as the bit stash of the output stage and as the coalescing tile of
     //  stage_channel_rows, both of which may run while the |L0| rows are live)
     static constexpr size_t kTileBytes = (size_t)FPW * (32 + MP) * 4;

@@ -110,6 +110,56 @@ struct ListDecoder {
     static constexpr uint32_t kDeadHigh = 0x7e000000u;                   // high word of 2^992: alive <=> high word below
     static __device__ __forceinline__ bool metric_alive(double m) { return (uint32_t)__double2hiint(m) < kDeadHigh; }
 
+    // Partial-sum state at the even phase phi_start, given the decided bits of all phases below it (prefix; bits at
+    // frozen phases are 0): for every set bit h of phi_start the left buffer of height h is the polar transform of the
+    // aligned 2^h-bit block that ends where the block of phi_start begins (scl.py:84-99 run to completion on that block).
+    // After stages 0..h-1 of the word-parallel transform every aligned 2^h block holds its own transform.
+    static __device__ __forceinline__ uint32_t word_at(const uint32_t (&x)[XW], int idx) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < XW; ++k) if (k == idx) v = x[k];
+        return v;
+    }
+    // one height of jump_partial_sums (H is a compile-time constant: the packed fields of bw are static)
+    template <int H>
+    static __device__ __forceinline__ void jump_level(const Code& code, PathT& p, uint32_t (&x)[XW], int phi_start) {
+        if constexpr (H < LOGMAX) {
+            if (H >= 1 && H < code.n && ((phi_start >> H) & 1)) {
+                const int o = phi_start & ~((2 << H) - 1);             // first phase of the finished left block of height H
+                constexpr int CW = ((1 << H) / 32) > 0 ? ((1 << H) / 32) : 1;
+                if constexpr (CW <= BW) {
+                    uint32_t cw[CW];
+                    if constexpr (H < 5) cw[0] = (word_at(x, o >> 5) >> (o & 31)) & ((1u << (1 << H)) - 1u);
+                    else {
+#pragma unroll
+                        for (int k = 0; k < CW; ++k) cw[k] = word_at(x, (o >> 5) + k);
+                    }
+                    store_height<H, BW, CW>(p.bw, cw);
+                }
+            }
+            // transform stage H (polar.py:17-29)
+            if constexpr (H < 5) {
+                constexpr uint32_t m = H == 0 ? 0x55555555u : H == 1 ? 0x33333333u : H == 2 ? 0x0f0f0f0fu : H == 3 ? 0x00ff00ffu : 0x0000ffffu;
+#pragma unroll
+                for (int w = 0; w < XW; ++w) x[w] ^= (x[w] >> (1 << H)) & m;
+            } else {
+                constexpr int d = 1 << (H - 5);
+#pragma unroll
+                for (int w = 0; w < XW; ++w) if ((w & d) == 0 && w + d < XW) x[w] ^= x[w + d];
+            }
+            jump_level<H + 1>(code, p, x, phi_start);
+        }
+    }
+    static __device__ __forceinline__ void jump_partial_sums(const Code& code, PathT& p, const uint32_t (&prefix)[XW], int phi_start) {
+        uint32_t x[XW];
+#pragma unroll
+        for (int w = 0; w < XW; ++w) {
+            const int lo = w * 32;
+            x[w] = prefix[w] & (phi_start >= lo + 32 ? 0xffffffffu : (phi_start <= lo ? 0u : ((1u << (phi_start - lo)) - 1u)));
+        }
+        jump_level<0>(code, p, x, phi_start);
+    }
+
     // Decode the FPW frames of this warp; `chanf` = wm.chan + (frame of this lane within the warp): the staged,
     // frame-interleaved channel row (element i at chanf[i * FPW], see stage_channel_rows).
     // fmask/fval (FORCED): per-frame masks over phases -- bit phi of fmask set <=> u_phi is forced to bit phi of
@@ -117,10 +167,21 @@ struct ListDecoder {
     // TRACE: also record, per information phase j, the leaf LLR every slot saw (wm.hist[j][lane]) and the slot each
     // surviving path came from (wm.lin[j][lane]); trace_walk() then yields a path's info_llrs (scl.py:159,167)
     // without the SC replay.
-    template <bool TRACE = false>
+    // JUMP (DL-SCL retries whose forced prefix is known, see dl_bin_kernel): the decode STARTS at the even phase
+    // phi_start (warp-uniform; every phase below it is forced for every frame of the warp).  The state the sequential
+    // schedule would have reached there is rebuilt directly: the partial sums are polar transforms of aligned blocks of
+    // the prefix bits (fval), and the LLR rows of the tree node that contains phi_start follow from one f / g level per
+    // height -- the same fp32 operations on the same inputs, so bit-identical to decoding the prefix -- by running the
+    // tree part of the "pseudo-phases" phi_start with its low bits cleared.  The path metric restarts at 0 at the
+    // frame's OWN start phase my_start (even, >= phi_start; below it the frame's single path is forced): the forced
+    // prefix adds the same constant to every path of the frame, and with the reset at my_start
+    // the result does not depend on which other frames share the warp.  jstart = number of information phases below
+    // phi_start (first trace row written).
+    template <bool TRACE = false, bool JUMP = false>
     static __device__ __forceinline__ void run(const Code& code, const uint32_t* __restrict__ imask, const WM& wm, PathT& p,
                                                int lane, const float* chanf, const uint32_t (&fmask)[XW],
-                                               const uint32_t (&fval)[XW], uint32_t& flags) {
+                                               const uint32_t (&fval)[XW], uint32_t& flags, int phi_start = 0, int jstart = 0,
+                                               int my_start = 0) {
         const int N = code.N;
         const uint32_t M = (uint32_t)code.M;
         const int slot = lane & (MP - 1), gbase = lane & ~(MP - 1);
@@ -133,19 +194,25 @@ struct ListDecoder {
         uint32_t tie = 0;
         uint32_t cur_info = 0, cur_fm = 0, cur_fv = 0;   // word phi/32 of the info / force masks
         float a = 0.f, b = 0.f;                          // height-1 pair of the current phase pair
-        int jinfo = 0;                                   // index of the current information phase (TRACE)
+        int jinfo = JUMP ? jstart : 0;                   // index of the current information phase (TRACE)
+        if constexpr (JUMP) {
+            if (phi_start > 0) jump_partial_sums(code, p, fval, phi_start);
+            cur_info = __ldg(imask + (phi_start >> 5)) >> (phi_start & 31);
+#pragma unroll
+            for (int k = 0; k < XW; ++k) if (k == (phi_start >> 5)) { cur_fm = fmask[k] >> (phi_start & 31); cur_fv = fval[k] >> (phi_start & 31); }
+        }
         // One phase.  R = 0..3: R = phi mod 4 is a compile-time constant, so the even/odd split, the height-1
         // recomputation of phases 2 (mod 4) and the one-level partial-sum update of phases 1 (mod 4) need no dispatch.
         // R = 10 / 11: even / odd phase of a pair whose kind (`half`) is a run-time, warp-uniform flag.
         // R < 0: everything is read from phi -- the
         // forced / trace-recording kernels keep the compact loop, their code is large enough as it is (measured:
         // the four-fold body costs them more in instruction fetch than the dispatch it removes).
-        auto phase = [&](const int phi, auto rc, const int half) {
+        auto phase = [&](const int phi, auto rc, const int half, const bool warm = false) {
             constexpr int R = decltype(rc)::value;
             // info / force masks as shift registers: bit 0 is the current phase (reloaded every 32 phases, shifted by one
             // at the end of every phase)
             if (R <= 0 || R == 10) {
-                if ((phi & 31) == 0) {
+                if ((phi & 31) == 0 && !(JUMP && warm)) {
                     cur_info = __ldg(imask + (phi >> 5));     // (a dynamic index into the by-value Code would force it into local memory)
                     if constexpr (FORCED) {
 #pragma unroll
@@ -161,6 +228,10 @@ struct ListDecoder {
                     if (half) pair_llr<true>(code, wm, p, phi, lane, chanf, a, b);
                     else pair_llr<false>(code, wm, p, phi, lane, chanf, a, b);
                 } else pair_llr<R == 2>(code, wm, p, phi, lane, chanf, a, b);
+                if constexpr (JUMP) {
+                    if (warm) return;                            // pseudo-phase of a jump start: LLR rows only
+                    if (phi == my_start) p.m = (MP == 1 || metric_alive(p.m)) ? 0.0 : p.m;
+                }
                 L = f_op(a, b);
             }
             else L = g_op_packed(a, b, p.bw[0], 0);              // u_{phi-1} sits in the height-0 field
@@ -296,8 +367,31 @@ struct ListDecoder {
 #ifndef PB_TRACE_FORM
 #define PB_TRACE_FORM 2
 #endif
-        constexpr int FORM = (!FORCED && !TRACE) ? (MP == 1 ? 4 : PB_LIST_FORM) : PB_TRACE_FORM;
-        if constexpr (FORM == 4) {
+        constexpr int FORM = JUMP ? 0 : (!FORCED && !TRACE) ? (MP == 1 ? 4 : PB_LIST_FORM) : PB_TRACE_FORM;
+        if constexpr (JUMP) {
+            // phases from phi_start on, preceded by the pseudo-phases {phi_start with its low bits cleared}: first the
+            // top bit alone (0 or N/2: height n-1 from the channel row by f or g), then one more set bit at a time.
+            // PB_JUMP_FORM 2: phase pairs (two copies of the phase body), 1: compact loop (one copy).
+#ifndef PB_JUMP_FORM
+#define PB_JUMP_FORM 2
+#endif
+            int phi0 = phi_start & (N >> 1);
+#pragma unroll 1
+            while (phi0 < N) {
+                const bool warm = phi0 < phi_start;
+                if constexpr (PB_JUMP_FORM == 2) {
+                    const int half = (phi0 >> 1) & 1;
+                    phase(phi0, std::integral_constant<int, 10>{}, half, warm);
+                    if (warm) { phi0 |= 1 << (31 - __clz(phi_start ^ phi0)); continue; }
+                    phase(phi0 + 1, std::integral_constant<int, 11>{}, half);
+                    phi0 += 2;
+                } else {
+                    phase(phi0, std::integral_constant<int, -1>{}, 0, warm);
+                    if (warm) phi0 |= 1 << (31 - __clz(phi_start ^ phi0));
+                    else ++phi0;
+                }
+            }
+        } else if constexpr (FORM == 4) {
 #pragma unroll 1
             for (int phi0 = 0; phi0 < N; phi0 += 4) {
                 phase(phi0, std::integral_constant<int, 0>{}, 0);
@@ -342,16 +436,16 @@ struct ListDecoder {
     // lineage chain (shared-memory reads only), then this lane's 32/MP trace loads back to back, then the sinks --
     // the global loads of a block are all in flight together instead of one L2 round trip per phase.
     template <typename Sink>
-    static __device__ __forceinline__ void trace_walk(const Code& code, const WM& wm, int lane, int end_lane, Sink&& sink) {
+    static __device__ __forceinline__ void trace_walk(const Code& code, const WM& wm, int lane, int end_lane, Sink&& sink, int jlow = 0) {
         const int slot = lane & (MP - 1), gbase = lane & ~(MP - 1);
         constexpr int PER = 32 / MP;                        // phases of a block this lane is responsible for
         int s = end_lane & (MP - 1);
-        for (int jtop = code.K - 1; jtop >= 0; jtop -= 32) {
+        for (int jtop = code.K - 1; jtop >= jlow; jtop -= 32) {      // (jlow > 0: the trace of a jump-started decode begins there)
             unsigned long long mine = 0;                    // slots of this lane's phases, 4 bits each, earliest phase lowest
 #pragma unroll
             for (int t = 0; t < 32; ++t) {
                 const int j = jtop - t;
-                if (j >= 0) {
+                if (j >= jlow) {
                     int w = 0;
                     if constexpr (MP > 1) {
                         const uint4 q = *reinterpret_cast<const uint4*>(wm.lin + j * 4);      // broadcast read
@@ -363,7 +457,7 @@ struct ListDecoder {
                 }
             }
             // this lane's phases of the block, ascending: j0, j0 + MP, ...
-            const int jlo = jtop - 31 > 0 ? jtop - 31 : 0;
+            const int jlo = jtop - 31 > jlow ? jtop - 31 : jlow;
             const int j0 = jlo + ((slot - jlo) & (MP - 1));
             float v[PER];
 #pragma unroll

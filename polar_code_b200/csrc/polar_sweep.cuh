@@ -94,6 +94,11 @@ struct SweepArgs {
     float* llr_store;              // [q_capacity][N] channel rows of the frames that entered the retry queue (Philox mode)
     float* abs_store;              // [q_capacity][K] |L0| of the baseline best path of every queued frame (flip.py:102)
     unsigned char* gscratch;       // per-warp global scratch (WarpMem::gbytes each)
+    // dl_bin_kernel: frames waiting for their next retry, binned by the information index they will flip
+    int* bin_ring;                 // [K][bin_cap] queue-entry indices (-1 = not written yet), one ring per flip index
+    unsigned int* bin_ctrl;        // 128-byte lines: [0] admission cursor, [32] finished frames, [64..72) statistics, [96 + 32 b + {0,1,2}] head / tail / fill of ring b
+    unsigned int bin_cap;          // ring capacity (power of two)
+    unsigned int inflight_target;  // frames admitted but not finished that the kernel tries to keep in the bins
 };
 
 // retry-queue entry: best u-hat of the latest attempt, tried set (by info index), the transmitted word (for the
@@ -448,6 +453,91 @@ struct Sweep {
         return slot;
     }
 
+    // rank_indices (flip.py:104-108): first untried index of argsort(|L0| @ beta) = argmin over untried.  `ab` = |L0| of
+    // the reference path of this group's frame (shared memory), `tried` = the frame's tried set (by info index).
+    // Returns the index to flip (0 for an invalid group); sets PB_FLAG_RANK_TIE in eflags when the best and the
+    // runner-up score are within 2e-6 relative.
+    static __device__ __forceinline__ int next_flip_index(const Code& code, const SweepArgs& a, const float* ab, const uint32_t (&tried)[XW],
+                                                          int lane, bool valid, uint32_t& eflags) {
+        const int K = code.K;
+        const int slot = lane & (MP - 1);
+        double m1 = 1e300, m2 = 1e300;
+        int a1 = 0x7fffffff;
+        auto offer = [&](double q, int j) {              // candidate score q of info index j (skipped when tried before)
+            uint32_t tw = 0;
+#pragma unroll
+            for (int w = 0; w < XW; ++w) if (w == (j >> 5)) tw = tried[w];
+            if (j < K && !((tw >> (j & 31)) & 1u)) {
+                if (q < m1 || (q == m1 && j < a1)) { m2 = m1; m1 = q; a1 = j; }
+                else if (q < m2) m2 = q;
+            }
+        };
+        if (a.beta64 != nullptr && MP >= 4) {
+            // q = |L0| @ beta of the warp's frames on the FP64 tensor cores: D[8 x 8] += A[8 x 4] B[4 x 8]
+            // (mma.m8n8k4.f64).  Row r = lane / 4 of A and D belongs to the frame of lane 4r (MP = 4: one row per frame;
+            // MP = 8: two identical rows per frame), so every lane loads |L0| of ITS OWN frame and receives scores of
+            // its own frame: A[r][k] = |L0|[i0 + lane % 4], B[k][n] = beta[i0 + lane % 4][j0 + lane / 4], and the lane
+            // ends up with columns j0 + 2 (lane % 4) + {0, 1}.  128 DMMAs replace 4 096 load + convert + DFMA triples
+            // per retry (flip.py:104-108 is K^2 multiply-adds; the summation order inside a DMMA differs from numpy's
+            // BLAS order as any other order would -- scores closer than 2e-6 relative are flagged PB_FLAG_RANK_TIE).
+            const int kq = lane & 3, nq = lane >> 2;
+            for (int j0 = 0; j0 < K; j0 += 8) {
+                double c0 = 0.0, c1 = 0.0;
+                const bool bj = j0 + nq < K;
+                const double* bp = a.beta64 + j0 + nq;
+                for (int i0 = 0; i0 < K; i0 += 4) {
+                    const int i = i0 + kq;
+                    const double av = i < K ? (double)ab[i] : 0.0;
+                    const double bv = (i < K && bj) ? __ldg(bp + (size_t)i * K) : 0.0;
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                 : "+d"(c0), "+d"(c1) : "d"(av), "d"(bv));
+                }
+                offer(c0, j0 + 2 * kq);
+                offer(c1, j0 + 2 * kq + 1);
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < XW; ++w) {
+                if (w * 32 < K) {
+                    double q[32 / MP];
+#pragma unroll
+                    for (int k = 0; k < 32 / MP; ++k) q[k] = 0.0;
+                    if (a.beta64) {
+                        for (int i = 0; i < K; ++i) {
+                            const double x = (double)ab[i];
+#pragma unroll
+                            for (int k = 0; k < 32 / MP; ++k) {
+                                const int j = w * 32 + slot + MP * k;
+                                if (j < K) q[k] += x * __ldg(&a.beta64[(size_t)i * K + j]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 32 / MP; ++k) {
+                            const int j = w * 32 + slot + MP * k;
+                            if (j < K) q[k] = (double)ab[j];
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 32 / MP; ++k) offer(q[k], w * 32 + slot + MP * k);
+                }
+            }
+        }
+        // (tensor-core path, MP = 8: lanes l and l ^ 4 hold the SAME columns of the same frame -- reducing over them too
+        //  would make every best score its own runner-up)
+        const int red = (a.beta64 != nullptr && MP >= 4) ? 4 : MP;
+#pragma unroll
+        for (int o = 1; o < MP; o <<= 1) {
+            if (o >= red) break;
+            const double om1 = __shfl_xor_sync(kFull, m1, o), om2 = __shfl_xor_sync(kFull, m2, o);
+            const int oa1 = __shfl_xor_sync(kFull, a1, o);
+            if (om1 < m1 || (om1 == m1 && oa1 < a1)) { m2 = fmin(m1, om2); m1 = om1; a1 = oa1; }
+            else m2 = fmin(m2, om1);
+        }
+        if (valid && m2 < 1e299 && (m2 - m1) <= 2e-6 * fmax(fabs(m1), fabs(m2))) eflags |= PB_FLAG_RANK_TIE;
+        return (valid && a1 < K) ? a1 : 0;
+    }
+
     static __device__ __forceinline__ void flush(const SweepArgs& a, int lane, const AccRef& acc) {
         if (a.counters == nullptr) return;
 #pragma unroll
@@ -573,7 +663,7 @@ __global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_retry_ker
     const size_t kWarpBytes = WM::bytes(code.N, code.K, code.K);
     wm.carve(smem + (size_t)warp * kWarpBytes, WM::warp_scratch(a.gscratch, code.N), code.N, code.K, WM::warp_trace(a.gscratch, code.N, code.K), code.K);
     const int slot = lane & (MP - 1), fme = lane / MP, gbase = lane & ~(MP - 1);
-    float* ab = wm.absl + fme * (code.K + 1);      // |L0| of the reference path of this group's frame
+    float* ab = wm.absl + fme * WM::absl_stride(code.K);      // |L0| of the reference path of this group's frame
     const bool leader = slot == 0;
     const int K = code.K;
     static_assert(cNum <= 12, "counter column");
@@ -628,82 +718,7 @@ __global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_retry_ker
             load_channel_ids<MP, WM>(code, tb, wm, row, lane);
         }
         const float* chanf = wm.chan + fme;
-        // rank_indices (flip.py:104-108): first untried index of argsort(|L0| @ beta) = argmin over untried
-        double m1 = 1e300, m2 = 1e300;
-        int a1 = 0x7fffffff;
-        auto offer = [&](double q, int j) {              // candidate score q of info index j (skipped when tried before)
-            uint32_t tw = 0;
-#pragma unroll
-            for (int w = 0; w < XW; ++w) if (w == (j >> 5)) tw = tried[w];
-            if (j < K && !((tw >> (j & 31)) & 1u)) {
-                if (q < m1 || (q == m1 && j < a1)) { m2 = m1; m1 = q; a1 = j; }
-                else if (q < m2) m2 = q;
-            }
-        };
-        if (a.beta64 != nullptr && MP >= 4) {
-            // q = |L0| @ beta of the warp's frames on the FP64 tensor cores: D[8 x 8] += A[8 x 4] B[4 x 8]
-            // (mma.m8n8k4.f64).  Row r = lane / 4 of A and D belongs to the frame of lane 4r (MP = 4: one row per frame;
-            // MP = 8: two identical rows per frame), so every lane loads |L0| of ITS OWN frame and receives scores of
-            // its own frame: A[r][k] = |L0|[i0 + lane % 4], B[k][n] = beta[i0 + lane % 4][j0 + lane / 4], and the lane
-            // ends up with columns j0 + 2 (lane % 4) + {0, 1}.  128 DMMAs replace 4 096 load + convert + DFMA triples
-            // per retry (flip.py:104-108 is K^2 multiply-adds; the summation order inside a DMMA differs from numpy's
-            // BLAS order as any other order would -- scores closer than 2e-6 relative are flagged PB_FLAG_RANK_TIE).
-            const int kq = lane & 3, nq = lane >> 2;
-            for (int j0 = 0; j0 < K; j0 += 8) {
-                double c0 = 0.0, c1 = 0.0;
-                const bool bj = j0 + nq < K;
-                const double* bp = a.beta64 + j0 + nq;
-                for (int i0 = 0; i0 < K; i0 += 4) {
-                    const int i = i0 + kq;
-                    const double av = i < K ? (double)ab[i] : 0.0;
-                    const double bv = (i < K && bj) ? __ldg(bp + (size_t)i * K) : 0.0;
-                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-                                 : "+d"(c0), "+d"(c1) : "d"(av), "d"(bv));
-                }
-                offer(c0, j0 + 2 * kq);
-                offer(c1, j0 + 2 * kq + 1);
-            }
-        } else {
-#pragma unroll
-            for (int w = 0; w < XW; ++w) {
-                if (w * 32 < K) {
-                    double q[32 / MP];
-#pragma unroll
-                    for (int k = 0; k < 32 / MP; ++k) q[k] = 0.0;
-                    if (a.beta64) {
-                        for (int i = 0; i < K; ++i) {
-                            const double x = (double)ab[i];
-#pragma unroll
-                            for (int k = 0; k < 32 / MP; ++k) {
-                                const int j = w * 32 + slot + MP * k;
-                                if (j < K) q[k] += x * __ldg(&a.beta64[(size_t)i * K + j]);
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 32 / MP; ++k) {
-                            const int j = w * 32 + slot + MP * k;
-                            if (j < K) q[k] = (double)ab[j];
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < 32 / MP; ++k) offer(q[k], w * 32 + slot + MP * k);
-                }
-            }
-        }
-        // (tensor-core path, MP = 8: lanes l and l ^ 4 hold the SAME columns of the same frame -- reducing over them too
-        //  would make every best score its own runner-up)
-        const int red = (a.beta64 != nullptr && MP >= 4) ? 4 : MP;
-#pragma unroll
-        for (int o = 1; o < MP; o <<= 1) {
-            if (o >= red) break;
-            const double om1 = __shfl_xor_sync(kFull, m1, o), om2 = __shfl_xor_sync(kFull, m2, o);
-            const int oa1 = __shfl_xor_sync(kFull, a1, o);
-            if (om1 < m1 || (om1 == m1 && oa1 < a1)) { m2 = fmin(m1, om2); m1 = om1; a1 = oa1; }
-            else m2 = fmin(m2, om1);
-        }
-        const int jf = (valid && a1 < K) ? a1 : 0;
-        if (valid && m2 < 1e299 && (m2 - m1) <= 2e-6 * fmax(fabs(m1), fabs(m2))) eflags |= PB_FLAG_RANK_TIE;
+        const int jf = S::next_flip_index(code, a, ab, tried, lane, valid, eflags);
         const int pf = (int)__ldg(&tb.info_pos[jf]);
         // _force_vector (flip.py:30-34): prefix of the reference bits, then the flipped bit, rest free
         uint32_t fm[XW], fv[XW];
@@ -740,6 +755,361 @@ __global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_retry_ker
             }
         }
         __syncwarp();
+    }
+    S::flush(a, lane, acc);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// DL-SCL retries, binned by flip position (the default retry kernel; dl_retry_kernel above is kept as the
+// reference implementation, PB200_DL_BINNED=0).
+//
+// A retry re-decodes the frame with the prefix of the latest best path forced and one bit flipped
+// (flip.py:30-62, scl.py:138-161).  Below the flipped phase exactly one path is alive and every decision is known,
+// so those phases only rebuild state the previous attempt already had: they are SKIPPED.  The decode jump-starts
+// at the flipped phase (ListDecoder::run<TRACE, JUMP>: partial sums from the prefix bits, one f / g level per tree
+// height from the channel row, metric restarting at 0), the leaf LLRs of the prefix phases are taken from the
+// frame's |L0| row (they were traced by the attempt that produced the prefix) and only rows >= the jump are
+// re-traced.  With the shipped beta the flipped position is nearly input-independent (attempt 1 flips info index 17
+// in 94 % of the frames, attempt 2 index 18, ...; mean flipped phase 66 of 128), so 40 % of the information phases and
+// half of the f / g work of a retry disappear -- provided the FPW frames of a warp start at the same phase, since the
+// schedule is warp-uniform.  Hence the bins: a frame waiting for its next attempt sits in the ring of the information
+// index it will flip; a warp pops FPW frames of ONE ring (or, when no ring holds a full batch, the highest rings,
+// starting at the lowest flipped phase of the batch), decodes them, scores the next flip (|L0| @ beta) and pushes
+// every unfinished frame into its next ring.  Frames therefore migrate between warps: their state lives in the queue
+// entry + the |L0| store (global, read with ld.cg after an acquire on the ring slot).
+//
+// Rings are multi-producer / multi-consumer and retry-free (thousands of warps pop the same ring at once):
+// push = atomicAdd on the tail, write the slot (it was -1), then atomicAdd on the ring's fill count;
+// pop = atomicSub of the wanted number from the fill count (anything beyond what was there is given back at once),
+// atomicAdd on the head for what was got, then wait for each claimed slot to be written and reset it to -1.
+// A frame enters a ring at most once (the tried set), at most inflight_target + resident frames are in the rings at
+// any time and bin_cap exceeds that, so a ring never wraps onto an unconsumed slot.
+// ---------------------------------------------------------------------------------------------------
+// polling loads of the scheduler words: relaxed, GPU scope (served by L2, never hoisted or cached in L1)
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) { unsigned int v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ int ld_volatile_s32(const int* p) { int v; asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+// Release store at GPU scope: everything this thread wrote (and what it observed through __syncwarp) is visible in L2
+// before the value is.  Unlike __threadfence() -- MEMBAR.SC + CCTL.IVALL, which throws away the whole L1 of the SM, beta
+// and the code tables with it, three times per batch -- it invalidates nothing; the consumers read with ld.cg (L2).
+__device__ __forceinline__ void st_release_s32(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+
+template <int MP, int LOGMAX, int NS = 0, int HS = 5>
+__global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_bin_kernel(const Code code_, const Tables tb, const SweepArgs a) {
+    const Code code = with_static_n<NS>(code_);
+    using S = Sweep<MP, LOGMAX, HS>;
+    using WM = WarpMem<MP, HS>;
+    using PathT = typename S::PathT;
+    using Entry = typename S::Entry;
+    constexpr int FPW = 32 / MP, XW = S::XW;
+    constexpr int EW = (int)(sizeof(Entry) / 8);                 // entry size in 8-byte words
+    static_assert(sizeof(Entry) % 8 == 0, "queue entries are moved as 8-byte words");
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    WM wm;
+    const size_t kWarpBytes = WM::bytes(code.N, code.K, code.K);
+    wm.carve(smem + (size_t)warp * kWarpBytes, WM::warp_scratch(a.gscratch, code.N), code.N, code.K, WM::warp_trace(a.gscratch, code.N, code.K), code.K);
+    const int slot = lane & (MP - 1), fme = lane / MP, gbase = lane & ~(MP - 1);
+    float* ab = wm.absl + fme * WM::absl_stride(code.K);
+    const bool leader = slot == 0;
+    const int K = code.K;
+    const AccRef acc{reinterpret_cast<uint32_t*>(smem + (size_t)wpc * kWarpBytes + (size_t)warp * acc_bytes(MP)) + lane / MP, FPW};
+    if (leader) {
+#pragma unroll
+        for (int c = 0; c < cNum; ++c) acc[c] = 0;
+    }
+    __syncwarp();
+    const unsigned int n_in = min(*a.q_in_count, a.q_capacity);
+    // control words, one 128-byte line each so that the rings do not share lines: cursor, finished count, statistics,
+    // then per ring {head, tail, fill}
+    unsigned int* cursor = a.bin_ctrl;
+    unsigned int* done = a.bin_ctrl + 32;
+    unsigned int* stats = a.bin_ctrl + 64;    // [0] waits, [1] lost claims, [2] batches, [3] frame decodes, [4] sum of phi_start, [5] mixed plans
+    auto ring_head = [&](int b) { return a.bin_ctrl + 96 + (size_t)b * 32; };
+    auto ring_tail = [&](int b) { return a.bin_ctrl + 96 + (size_t)b * 32 + 1; };
+    auto ring_fill = [&](int b) { return reinterpret_cast<int*>(a.bin_ctrl + 96 + (size_t)b * 32 + 2); };
+    const unsigned int cap_mask = a.bin_cap - 1;
+    // per-warp scratch of the scheduler in the (dead between decodes) tree rows: ring fill counts, the batch plan
+    unsigned int* cnt = reinterpret_cast<unsigned int*>(wm.ts);              // [K]
+    int* plan = reinterpret_cast<int*>(wm.xchg);                             // [FPW] ring of each group (-1 none)
+    unsigned int* ppos = reinterpret_cast<unsigned int*>(wm.xchg) + 32;      // [FPW] claimed ring position
+    int* pok = reinterpret_cast<int*>(wm.xchg) + 64;                         // [FPW] position valid
+    Entry* const entries = reinterpret_cast<Entry*>(a.q_in);
+
+    // score the next flip of this group's frame from ab[] and queue it (group-uniform arguments).  The leaders of a warp
+    // that push into the same ring share one atomicAdd on its tail and one on its fill count.
+    auto push_next = [&](bool go, long long eidx, const uint32_t (&tried)[XW], uint32_t eflags) {
+        uint32_t fl = eflags;
+        const int jn = S::next_flip_index(code, a, ab, tried, lane, go, fl);
+        const bool me = go && leader;
+        if (me && fl != eflags) entries[eidx].h.flags = fl;                  // PB_FLAG_RANK_TIE of this ranking
+        __syncwarp();                                                         // the group's |L0| stores happen before the leader's release
+        const uint32_t peers = __match_any_sync(kFull, me ? jn : -1 - lane);  // leaders pushing into the same ring
+        const int first = __ffs(peers) - 1;
+        unsigned int base = 0;
+        if (me && lane == first) base = atomicAdd(ring_tail(jn), (unsigned int)__popc(peers));
+        base = __shfl_sync(kFull, base, first);
+        if (me) {
+            const unsigned int pos = base + __popc(peers & ((1u << lane) - 1u));
+            int* sl = a.bin_ring + (size_t)jn * a.bin_cap + (pos & cap_mask);
+            while (ld_volatile_s32(sl) != -1) __nanosleep(100);               // (never taken: see the capacity argument above)
+            st_release_s32(sl, (int)eidx);                                    // entry + |L0| row before the ring slot
+        }
+        if (me && lane == first) atomicAdd(ring_fill(jn), __popc(peers));         // (a claim that overtakes the slot write waits on the slot)
+    };
+
+    // Scheduler: ONE warp per CTA talks to the rings and claims work for the whole CTA (FPW frames per warp), the other
+    // warps wait at a barrier -- 148 pollers instead of 4 736, two atomics per CTA step on the ring's own cache line,
+    // and the warps of a CTA decode the same ring in lock step (same start phase, same instruction stream).
+    // Fast path: keep popping the ring popped last, so rings are drained one after the other and the frames advance level
+    // by level.  Slow path, when that ring runs dry: read the cursor, the finished count and every ring's fill count,
+    // then leave / admit new frames / pick the fullest ring (or, when no ring holds FPW frames, the highest rings) / wait.
+    __shared__ int s_cmd;                     // 0 decode, 1 admit, 2 leave
+    __shared__ unsigned int s_base;           // admission: first queue entry of this CTA step
+    __shared__ int s_plan[1024];              // ring of each frame slot of the CTA (-1 none)
+    __shared__ unsigned int s_pos[1024];      // claimed ring position
+    __shared__ unsigned char s_ok[1024];      // position valid
+    const int CTA_F = FPW * wpc;
+    unsigned int st_batches = 0, st_decodes = 0, st_phi = 0, st_mixed = 0;
+    unsigned int backoff = 500u;
+    int sticky = -1;                          // (scheduler warp only)
+    for (;;) {
+        bool push_go = false;                 // what the common tail of the iteration pushes (one call site)
+        long long push_idx = -1;
+        uint32_t push_flags = 0;
+        uint32_t tried[XW];
+#pragma unroll
+        for (int k = 0; k < XW; ++k) tried[k] = 0;
+        if (warp == 0) {
+            int cmd = 0;
+            unsigned int base = 0;
+            // claim up to CTA_F frames of ring b; fills the CTA plan; returns the number got
+            auto claim_ring = [&](int b) -> int {
+                int got = 0;
+                unsigned int h = 0;
+                if (lane == 0) {
+                    const int had = atomicSub(ring_fill(b), CTA_F);
+                    got = had >= CTA_F ? CTA_F : (had > 0 ? had : 0);
+                    if (got < CTA_F) atomicAdd(ring_fill(b), CTA_F - got);
+                    if (got > 0) h = atomicAdd(ring_head(b), (unsigned int)got);
+                }
+                got = __shfl_sync(kFull, got, 0); h = __shfl_sync(kFull, h, 0);
+                for (int i = lane; i < CTA_F; i += 32) { s_plan[i] = b; s_ok[i] = i < got; s_pos[i] = h + i; }
+                return got;
+            };
+            for (;;) {
+                if (sticky >= 0) {
+                    const int got = claim_ring(sticky);
+                    if (got < CTA_F) sticky = -1;                             // ran dry: look around next time
+                    if (got > 0) { cmd = 0; break; }
+                }
+                // one round trip: cursor, finished count and the fill counts of all rings (transiently negative while a
+                // pop gives back what it could not get)
+                unsigned int cur = 0, fin = 0;
+                if (lane == 0) { cur = ld_volatile_u32(cursor); fin = ld_volatile_u32(done); }
+                unsigned int bestc = 0, total = 0;
+                int bestb = 0;
+                {
+                    constexpr int NB = (1 << LOGMAX) / 32;                    // K <= N: NB loads per lane, all in flight together
+                    int f[NB];
+#pragma unroll
+                    for (int i = 0; i < NB; ++i) f[i] = (i * 32 + lane < K) ? ld_volatile_s32(ring_fill(i * 32 + lane)) : 0;
+#pragma unroll
+                    for (int i = 0; i < NB; ++i) {
+                        const int b = i * 32 + lane;
+                        const unsigned int c = f[i] > 0 ? (unsigned int)f[i] : 0u;
+                        if (b < K) cnt[b] = c;
+                        total += c;
+                        if (c > bestc) { bestc = c; bestb = b; }
+                    }
+                }
+                cur = __shfl_sync(kFull, cur, 0); fin = __shfl_sync(kFull, fin, 0);
+                if (fin >= n_in) { cmd = 2; break; }
+                const unsigned int admitted = cur < n_in ? cur : n_in;
+                if (cur < n_in && admitted - fin < a.inflight_target) {
+                    if (lane == 0) base = atomicAdd(cursor, (unsigned int)CTA_F);
+                    base = __shfl_sync(kFull, base, 0);
+                    cmd = 1;
+                    break;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const unsigned int oc = __shfl_xor_sync(kFull, bestc, o);
+                    const int ob = __shfl_xor_sync(kFull, bestb, o);
+                    total += __shfl_xor_sync(kFull, total, o);
+                    if (oc > bestc || (oc == bestc && ob > bestb)) { bestc = oc; bestb = ob; }
+                }
+                int got_any = 0;
+                if (total > 0) {
+                    __syncwarp();
+                    if (bestc >= (unsigned int)FPW) {
+                        const int got = claim_ring(bestb);
+                        if (got == CTA_F) sticky = bestb;
+                        got_any = got;
+                    } else {
+                        // no ring holds a warp's worth: the highest rings first (similar start phases end up in one warp)
+                        if (lane == 0) {
+                            int g = 0;
+                            for (int b = K - 1; b >= 0 && g < CTA_F; --b)
+                                for (unsigned int c = cnt[b]; c > 0 && g < CTA_F; --c) s_plan[g++] = b;
+                            for (; g < CTA_F; ++g) s_plan[g] = -1;
+                            g = 0;
+                            while (g < CTA_F) {                               // one claim per run of equal rings
+                                const int b = s_plan[g];
+                                if (b < 0) { s_ok[g] = 0; ++g; continue; }
+                                int n = 1;
+                                while (g + n < CTA_F && s_plan[g + n] == b) ++n;
+                                const int had = atomicSub(ring_fill(b), n);
+                                const int got = had >= n ? n : (had > 0 ? had : 0);
+                                if (got < n) atomicAdd(ring_fill(b), n - got);
+                                unsigned int h = 0;
+                                if (got > 0) h = atomicAdd(ring_head(b), (unsigned int)got);
+                                for (int i = 0; i < n; ++i) { s_ok[g + i] = i < got; s_pos[g + i] = h + i; }
+                                got_any += got;
+                                g += n;
+                            }
+                        }
+                        got_any = __shfl_sync(kFull, got_any, 0);
+                    }
+                }
+                if (got_any > 0) { cmd = 0; break; }
+                if (lane == 0) atomicAdd(&stats[total == 0 ? 0 : 1], 1u);      // frames are in flight elsewhere / lost the race
+                __nanosleep(backoff);
+                backoff = backoff < 8000u ? backoff * 2u : backoff;
+            }
+            backoff = 500u;
+            if (lane == 0) { s_cmd = cmd; s_base = base; }
+        }
+        __syncthreads();
+        const int cmd = s_cmd;
+        if (cmd == 2) break;
+        const int myi = warp * FPW + fme;                                     // this group's frame slot in the CTA plan
+        const int myb = s_plan[myi];
+        bool valid = cmd == 0 && s_ok[myi] != 0;
+        const unsigned int mypos = s_pos[myi];
+        const unsigned int adm_base = s_base;
+        __syncthreads();                                                      // the plan may be rewritten from here on
+        if (cmd == 1) {
+            // admission: the first ranking of the frames the baseline pass queued (their |L0| rows are in abs_store)
+            push_idx = (long long)adm_base + myi;
+            push_go = push_idx < (long long)n_in;
+            if (push_go) {
+                push_flags = __ldcg(&entries[push_idx].h.flags);
+                const float* src = a.abs_store + push_idx * (long long)K;
+                for (int j = slot; j < K; j += MP) ab[j] = __ldcg(src + j);
+            }
+        } else if (__any_sync(kFull, valid)) {
+        long long eidx = -1;
+        if (valid && leader) {
+            int* sl = a.bin_ring + (size_t)myb * a.bin_cap + (mypos & cap_mask);
+            int v;
+            while ((v = ld_volatile_s32(sl)) < 0) __nanosleep(50);
+            *reinterpret_cast<volatile int*>(sl) = -1;
+            eidx = v;                                                         // the entry / |L0| loads below depend on it and read L2 (ld.cg)
+        }
+        eidx = __shfl_sync(kFull, eidx, gbase);
+        __syncwarp();
+
+        // ---- the frames of this batch ----------------------------------------------------------------------
+        long long my_frame = -1, store = 0;
+        uint32_t eflags = 0, n_tried = 0;
+        uint32_t u_ref[XW], u_sent[XW];
+#pragma unroll
+        for (int k = 0; k < XW; ++k) { u_ref[k] = 0; u_sent[k] = 0; }
+        if (valid) {
+            unsigned long long w[EW];
+            const unsigned long long* ep = reinterpret_cast<const unsigned long long*>(entries + eidx);
+#pragma unroll
+            for (int k = 0; k < EW; ++k) w[k] = __ldcg(ep + k);
+            Entry e;
+            memcpy(&e, w, sizeof(Entry));
+            my_frame = e.h.frame; eflags = e.h.flags; n_tried = e.h.n_tried; store = e.store;
+#pragma unroll
+            for (int k = 0; k < XW; ++k) { u_ref[k] = e.u[k]; tried[k] = e.tried[k]; u_sent[k] = e.u_sent[k]; }
+        }
+        {
+            const float* row = nullptr;
+            // (sweep mode: the LLR-store row of a frame is its queue slot, so the row loads do not wait for the entry)
+            if (valid) row = (a.llr == nullptr) ? a.llr_store + eidx * (long long)code.N
+                                                : a.llr + (my_frame - a.frame_begin) * (long long)a.in_len;
+            load_channel_ids<MP, WM>(code, tb, wm, row, lane);
+        }
+        const float* chanf = wm.chan + fme;
+        const int jf = valid ? myb : 0;                                       // the ring IS the index to flip
+        const int pf = (int)__ldg(&tb.info_pos[jf]);
+        // start of the warp's decode: the lowest flipped phase of the batch, rounded down to a phase pair
+        int pmin = valid ? pf : code.N;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) pmin = min(pmin, __shfl_xor_sync(kFull, pmin, o));
+        const int phi_start = pmin & ~1;
+        {   // statistics of this warp (flushed once, at the end)
+            const uint32_t vm = __ballot_sync(kFull, valid && leader);
+            const uint32_t same = __ballot_sync(kFull, !valid || pf == pmin);
+            st_batches += 1; st_decodes += __popc(vm); st_phi += (unsigned int)phi_start; st_mixed += same != kFull ? 1u : 0u;
+        }
+        int jstart = 0;
+#pragma unroll
+        for (int w = 0; w < XW; ++w) {
+            const int lo = w * 32;
+            const uint32_t below = (phi_start >= lo + 32) ? 0xffffffffu : (phi_start <= lo ? 0u : ((1u << (phi_start - lo)) - 1u));
+            jstart += __popc(code.info_mask[w] & below);
+        }
+        // _force_vector (flip.py:30-34): prefix of the reference bits, then the flipped bit, rest free
+        uint32_t fm[XW], fv[XW];
+#pragma unroll
+        for (int w = 0; w < XW; ++w) {
+            const int lo = w * 32;
+            const uint32_t below = (pf >= lo + 32) ? 0xffffffffu : (pf <= lo ? 0u : ((1u << (pf - lo)) - 1u));
+            const uint32_t bit = (pf >= lo && pf < lo + 32) ? (1u << (pf - lo)) : 0u;
+            fm[w] = code.info_mask[w] & (below | bit);
+            fv[w] = (u_ref[w] & below) | (~u_ref[w] & bit);
+            if (valid && jf >= lo && jf < lo + 32) tried[w] |= 1u << (jf - lo);      // tried set is indexed by info index
+        }
+        if (valid) n_tried += 1;
+        if (leader && valid && a.tried) a.tried[(my_frame - a.frame_begin) * (long long)a.R + (n_tried - 1)] = jf;
+        uint32_t flags = 0;
+        PathT p;
+        S::DecF::init(p, lane, valid);
+        S::DecF::template run<true, true>(code, tb.info_mask, wm, p, lane, chanf, fm, fv, flags, phi_start, jstart, pf & ~1);   // retry_with_flip (flip.py:37-62)
+        typename S::Best b;
+        S::pick_best(code, tb, p, lane, flags | eflags, b);
+        bool more = false;
+        if (valid) {
+            if (leader) acc[cNearTie] += ((b.flags & PB_FLAG_NEAR_TIE) && !(eflags & PB_FLAG_NEAR_TIE)) ? 1u : 0u;
+            const bool pass = code.crc_deg == 0 ? true : b.pass;
+            more = !(pass || (int)n_tried >= a.retries || (int)n_tried >= K);          // flip.py:111,134
+            if (!more && leader) S::finish_dl(code, tb, a, wm, lane, my_frame, b, n_tried, u_sent, acc);
+        }
+        {
+            const uint32_t fmask_done = __ballot_sync(kFull, valid && !more && leader);
+            if (lane == 0 && fmask_done) atomicAdd(done, (unsigned int)__popc(fmask_done));
+        }
+        __syncwarp();
+        if (more) {
+            // the next attempt starts from THIS attempt's best path (flip.py:127-133): new entry, new |L0| rows >= jstart
+            if (leader) {
+                Entry e;
+                e.h.frame = my_frame; e.h.flags = b.flags; e.h.n_tried = n_tried;
+#pragma unroll
+                for (int k = 0; k < XW; ++k) { e.u[k] = b.u[k]; e.tried[k] = tried[k]; e.u_sent[k] = u_sent[k]; }
+                e.store = (uint32_t)store; e.pad = 0;
+                unsigned long long w[EW];
+                memcpy(w, &e, sizeof(Entry));
+                unsigned long long* ep = reinterpret_cast<unsigned long long*>(entries + eidx);
+#pragma unroll
+                for (int k = 0; k < EW; ++k) ep[k] = w[k];
+            }
+            float* dst = a.abs_store + eidx * (long long)K;
+            S::DecF::trace_walk(code, wm, lane, b.lane, [&](int j, float L) { const float v = fabsf(L); ab[j] = v; dst[j] = v; }, jstart);   // flip.py:133
+            for (int j = slot; j < jstart; j += MP) ab[j] = __ldcg(dst + j);          // prefix rows: traced by earlier attempts
+        }
+        push_go = more; push_idx = eidx; push_flags = b.flags;
+        }   // (decode path)
+        __syncwarp();
+        push_next(push_go, push_idx, tried, push_flags);
+        __syncwarp();
+    }
+    if (lane == 0 && st_batches) {
+        atomicAdd(&stats[2], st_batches); atomicAdd(&stats[3], st_decodes); atomicAdd(&stats[4], st_phi); atomicAdd(&stats[5], st_mixed);
     }
     S::flush(a, lane, acc);
 }
