@@ -255,6 +255,9 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
                     e->d_bin_ring = nullptr; e->bin_ring_bytes = 0;
                     CUDA_TRY(cudaMalloc((void**)&e->d_bin_ring, ring_bytes));
                     e->bin_ring_bytes = ring_bytes;
+                    // all slots empty (-1).  Every pop resets its slot, so a finished launch leaves the rings empty again and
+                    // they are initialised only here
+                    CUDA_TRY(cudaMemsetAsync(e->d_bin_ring, 0xff, ring_bytes, st));
                 }
                 if (e->bin_ctrl_n < 96 + 32 * K) {
                     cudaFree(e->d_bin_ctrl);
@@ -262,7 +265,6 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
                     CUDA_TRY(cudaMalloc((void**)&e->d_bin_ctrl, sizeof(unsigned int) * (96 + 32 * K)));
                     e->bin_ctrl_n = 96 + 32 * K;
                 }
-                CUDA_TRY(cudaMemsetAsync(e->d_bin_ring, 0xff, ring_bytes, st));
                 CUDA_TRY(cudaMemsetAsync(e->d_bin_ctrl, 0, sizeof(unsigned int) * (96 + 32 * K), st));
                 q.bin_ring = e->d_bin_ring;
                 q.bin_ctrl = e->d_bin_ctrl;

@@ -236,6 +236,38 @@ __device__ __forceinline__ void stage_channel_rows(const WM& wm, int N, int lane
         __syncwarp();
     }
 }
+// The same for whole rows at once, when the tile [FPW][N + MP] fits the tree + exchange area (N = 128: MP >= 4) and every
+// row is 16-byte aligned: each row arrives with ONE 16-byte cp.async per lane (global -> shared, no registers, all FPW
+// rows in flight together -- one DRAM round trip instead of one per 32 columns), then the tile is written out
+// frame-interleaved as full 128 B lines.  Returns false (nothing done) when the conditions do not hold.
+template <int MP, typename WM>
+__device__ __forceinline__ bool stage_channel_rows_async(const WM& wm, int N, int lane, const float* row /* this lane's frame */) {
+    constexpr int FPW = 32 / MP;
+    const int TS = N + MP;
+    if ((size_t)FPW * TS * 4 > WM::kTreeBytes + kXchgBytes || (N & 127) != 0) return false;
+    const bool ok = row == nullptr || (reinterpret_cast<uintptr_t>(row) & 15) == 0;
+    if (!__all_sync(kFull, ok)) return false;
+    float* tile = wm.ts;
+    for (int c0 = 0; c0 < N; c0 += 128) {
+#pragma unroll
+        for (int f = 0; f < FPW; ++f) {
+            const float* r = reinterpret_cast<const float*>(__shfl_sync(kFull, (unsigned long long)reinterpret_cast<uintptr_t>(row), f * MP));
+            float* d = tile + f * TS + c0 + 4 * lane;
+            if (r != nullptr) {
+                const unsigned int sa = (unsigned int)__cvta_generic_to_shared(d);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(r + c0 + 4 * lane) : "memory");
+            } else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    for (int t = lane; t < FPW * N; t += 32) {
+        const int f = t & (FPW - 1), di = t / FPW;
+        wm.chan[t] = tile[f * TS + di];                       // chan[di * FPW + f]; bank of the read = f * MP + di (mod 32): conflict-free
+    }
+    __syncwarp();
+    return true;
+}
 // The common case: the FPW rows are CONTIGUOUS in memory (frames g*FPW .. g*FPW+FPW-1 of a [B, N] buffer), all valid and
 // N is a multiple of 32 -- no per-row pointers, no guards.
 template <int MP, typename WM>

@@ -312,12 +312,15 @@ __device__ __forceinline__ const float* shfl_ptr(const float* p, int src) {
 // Stage the channel LLRs of arbitrary frames (LLR-in mode): `row` = this lane's frame's row in the caller's buffer
 // (nullptr = none).  Plain rows go through the coalescing tile; with NR rate matching the de-rate-matched row is
 // gathered (rate_match.py:19-39, interleaver.py:26-37) straight into the frame-interleaved layout.
-template <int MP, typename WM>
+// WHOLE_ROWS: the whole tree + exchange area of the warp is free (no |L0| rows live), so plain rows may be fetched in one go.
+template <int MP, typename WM, bool WHOLE_ROWS = false>
 __device__ __forceinline__ void load_channel_ids(const Code& code, const Tables& tb, const WM& wm, const float* row, int lane) {
     constexpr int FPW = 32 / MP;
     const int N = code.N;
     if (tb.E == 0) {
-        stage_channel_rows<MP>(wm, N, lane, [&](int f) { return shfl_ptr(row, f * MP); });
+        bool done = false;
+        if constexpr (WHOLE_ROWS) done = stage_channel_rows_async<MP>(wm, N, lane, row);
+        if (!done) stage_channel_rows<MP>(wm, N, lane, [&](int f) { return shfl_ptr(row, f * MP); });
         return;
     }
     for (int e = lane; e < FPW * N; e += 32) {
@@ -584,7 +587,7 @@ __global__ void __launch_bounds__(PB_SWEEP_THREADS) sweep_kernel(const Code code
         if (a.llr) {
 #pragma unroll
             for (int k = 0; k < XW; ++k) u_sent[k] = 0;
-            load_channel_ids<MP, WM>(code, tb, wm, valid ? a.llr + idx * (long long)a.in_len : nullptr, lane);
+            load_channel_ids<MP, WM, true>(code, tb, wm, valid ? a.llr + idx * (long long)a.in_len : nullptr, lane);
         } else {
             gen_channel<MP, XW, WM>(code, tb, a.cc, wm, my_frame, lane, u_sent, unc, true);
         }
@@ -870,6 +873,8 @@ __global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_bin_kerne
     __shared__ unsigned char s_ok[1024];      // position valid
     const int CTA_F = FPW * wpc;
     unsigned int st_batches = 0, st_decodes = 0, st_phi = 0, st_mixed = 0;
+    unsigned long long st_sched_ns = 0, t_kernel0 = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_kernel0));
     unsigned int backoff = 500u;
     int sticky = -1;                          // (scheduler warp only)
     for (;;) {
@@ -882,6 +887,8 @@ __global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_bin_kerne
         if (warp == 0) {
             int cmd = 0;
             unsigned int base = 0;
+            unsigned long long t_sched0 = 0;
+            if (lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_sched0));
             // claim up to CTA_F frames of ring b; fills the CTA plan; returns the number got
             auto claim_ring = [&](int b) -> int {
                 int got = 0;
@@ -978,6 +985,10 @@ __global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_bin_kerne
             }
             backoff = 500u;
             if (lane == 0) { s_cmd = cmd; s_base = base; }
+            if (lane == 0) {                                                  // statistics: time this CTA's scheduler spent
+                unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                st_sched_ns += t1 - t_sched0;
+            }
         }
         __syncthreads();
         const int cmd = s_cmd;
@@ -1031,7 +1042,7 @@ __global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_bin_kerne
             // (sweep mode: the LLR-store row of a frame is its queue slot, so the row loads do not wait for the entry)
             if (valid) row = (a.llr == nullptr) ? a.llr_store + eidx * (long long)code.N
                                                 : a.llr + (my_frame - a.frame_begin) * (long long)a.in_len;
-            load_channel_ids<MP, WM>(code, tb, wm, row, lane);
+            load_channel_ids<MP, WM, true>(code, tb, wm, row, lane);
         }
         const float* chanf = wm.chan + fme;
         const int jf = valid ? myb : 0;                                       // the ring IS the index to flip
@@ -1107,6 +1118,11 @@ __global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_bin_kerne
         __syncwarp();
         push_next(push_go, push_idx, tried, push_flags);
         __syncwarp();
+    }
+    if (warp == 0 && lane == 0) {
+        unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        atomicMax(&stats[6], (unsigned int)(st_sched_ns >> 10));              // longest scheduler time of a CTA (~us)
+        atomicMax(&stats[7], (unsigned int)((t1 - t_kernel0) >> 10));         // longest CTA lifetime (~us)
     }
     if (lane == 0 && st_batches) {
         atomicAdd(&stats[2], st_batches); atomicAdd(&stats[3], st_decodes); atomicAdd(&stats[4], st_phi); atomicAdd(&stats[5], st_mixed);

@@ -22,7 +22,7 @@ st = (C.c_uint * 8)()
 eng.lib.pb200_debug_bin_stats(eng._h, st)
 s = list(st)
 print(f"M={M} snr={snr} B={B}: best {min(ts[2:]):.3f} ms median {np.median(ts[2:]):.3f} ms -> {B / np.median(ts[2:]) * 1e3:.4g} frames/s | waits {s[0]} lost {s[1]} batches {s[2]} decodes {s[3]} "
-      f"(fill {s[3] / max(s[2], 1):.2f}/{32 // max(M, 1) if M in (1, 2, 4, 8) else '?'}) mean start phase {s[4] / max(s[2], 1):.1f} mixed {s[5]}")
+      f"(fill {s[3] / max(s[2], 1):.2f}/{32 // max(M, 1) if M in (1, 2, 4, 8) else '?'}) mean start phase {s[4] / max(s[2], 1):.1f} mixed {s[5]} max-sched {s[6] * 1.024e-3:.2f} ms cta-life {s[7] * 1.024e-3:.2f} ms | all {[round(t, 1) for t in ts]}")
 if "--trace" in sys.argv:
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
