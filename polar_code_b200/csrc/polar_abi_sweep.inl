@@ -131,12 +131,16 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
     const bool big = e->code.n > 7;
     Code code = e->code;
     code.M = M;
-    // with retries the baseline pass records the leaf-LLR trace and writes |L0| of every queued frame (kind 2)
-    const bool trace = a.retries > 0;
-    auto pick = [&](int kind) { return big ? pb_sweep_kernel_9(MP, kind) : code.n == 7 ? pb_sweep_kernel_7s(MP, kind) : pb_sweep_kernel_7(MP, kind); };
-    const void* base = pick(trace ? 2 : 0);
     if (e->dl_binned < 0) { const char* env = getenv("PB200_DL_BINNED"); e->dl_binned = (env && env[0] == '0') ? 0 : 1; }
     const bool binned = e->dl_binned != 0;
+    // Frame-per-group retry kernel: the baseline pass records the leaf-LLR trace and writes |L0| of every queued frame
+    // (kind 2).  Binned retry kernel: the baseline pass is the plain one -- queued frames get their first |L0| row from an
+    // "attempt 0" replay inside the retry kernel, so the frames that pass (most of them) never pay for a trace.
+    bool replay = binned;
+    if (const char* env = getenv("PB200_DL_REPLAY")) replay = binned && env[0] != '0';
+    const bool trace = a.retries > 0 && !replay;
+    auto pick = [&](int kind) { return big ? pb_sweep_kernel_9(MP, kind) : code.n == 7 ? pb_sweep_kernel_7s(MP, kind) : pb_sweep_kernel_7(MP, kind); };
+    const void* base = pick(trace ? 2 : 0);
     const void* round = pick(binned ? 3 : 1);
     KernelCfg kb, kr{};
     int rc = choose_cfg(e, base, MP, trace ? 6 : 4, warp_bytes(MP, code.N, 0, false, trace ? code.K : 0) + acc_bytes(MP), &kb);
@@ -266,6 +270,7 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
                     e->bin_ctrl_n = 96 + 32 * K;
                 }
                 CUDA_TRY(cudaMemsetAsync(e->d_bin_ctrl, 0, sizeof(unsigned int) * (96 + 32 * K), st));
+                q.replay_admission = replay ? 1 : 0;
                 q.bin_ring = e->d_bin_ring;
                 q.bin_ctrl = e->d_bin_ctrl;
             }

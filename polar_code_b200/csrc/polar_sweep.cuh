@@ -99,6 +99,7 @@ struct SweepArgs {
     unsigned int* bin_ctrl;        // 128-byte lines: [0] admission cursor, [32] finished frames, [64..72) statistics, [96 + 32 b + {0,1,2}] head / tail / fill of ring b
     unsigned int bin_cap;          // ring capacity (power of two)
     unsigned int inflight_target;  // frames admitted but not finished that the kernel tries to keep in the bins
+    int replay_admission;          // 1: the baseline pass left no |L0| rows, admission replays the baseline decode with the trace on
 };
 
 // retry-queue entry: best u-hat of the latest attempt, tried set (by info index), the transmitted word (for the
@@ -999,8 +1000,15 @@ __global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_bin_kerne
         const unsigned int mypos = s_pos[myi];
         const unsigned int adm_base = s_base;
         __syncthreads();                                                      // the plan may be rewritten from here on
-        if (cmd == 1) {
-            // admission: the first ranking of the frames the baseline pass queued (their |L0| rows are in abs_store)
+        // Admission (cmd 1): the baseline pass queued these frames WITHOUT a trace (tracing every frame costs a quarter of
+        // the baseline pass, and most frames never need it).  Their first |L0| row comes from replaying the baseline
+        // decode here, trace on, nothing forced -- "attempt 0", the same decode bit for bit -- after which they are
+        // ranked and queued like any other attempt.
+        // (replay_admission = 0: the baseline pass traced every frame and left the |L0| rows in abs_store; admission then
+        //  only ranks them)
+        const bool fresh = cmd == 1 && a.replay_admission != 0;
+        long long eidx = -1;
+        if (cmd == 1 && !fresh) {
             push_idx = (long long)adm_base + myi;
             push_go = push_idx < (long long)n_in;
             if (push_go) {
@@ -1008,16 +1016,18 @@ __global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_bin_kerne
                 const float* src = a.abs_store + push_idx * (long long)K;
                 for (int j = slot; j < K; j += MP) ab[j] = __ldcg(src + j);
             }
-        } else if (__any_sync(kFull, valid)) {
-        long long eidx = -1;
-        if (valid && leader) {
+        } else if (fresh) {
+            eidx = (long long)adm_base + myi;
+            valid = eidx < (long long)n_in;
+        } else if (valid && leader) {
             int* sl = a.bin_ring + (size_t)myb * a.bin_cap + (mypos & cap_mask);
             int v;
             while ((v = ld_volatile_s32(sl)) < 0) __nanosleep(50);
             *reinterpret_cast<volatile int*>(sl) = -1;
             eidx = v;                                                         // the entry / |L0| loads below depend on it and read L2 (ld.cg)
         }
-        eidx = __shfl_sync(kFull, eidx, gbase);
+        if (__any_sync(kFull, valid)) {
+        if (!fresh) eidx = __shfl_sync(kFull, eidx, gbase);
         __syncwarp();
 
         // ---- the frames of this batch ----------------------------------------------------------------------
@@ -1045,8 +1055,8 @@ __global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_bin_kerne
             load_channel_ids<MP, WM, true>(code, tb, wm, row, lane);
         }
         const float* chanf = wm.chan + fme;
-        const int jf = valid ? myb : 0;                                       // the ring IS the index to flip
-        const int pf = (int)__ldg(&tb.info_pos[jf]);
+        const int jf = (valid && !fresh) ? myb : 0;                           // the ring IS the index to flip
+        const int pf = fresh ? 0 : (int)__ldg(&tb.info_pos[jf]);
         // start of the warp's decode: the lowest flipped phase of the batch, rounded down to a phase pair
         int pmin = valid ? pf : code.N;
 #pragma unroll
@@ -1071,12 +1081,12 @@ __global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_bin_kerne
             const int lo = w * 32;
             const uint32_t below = (pf >= lo + 32) ? 0xffffffffu : (pf <= lo ? 0u : ((1u << (pf - lo)) - 1u));
             const uint32_t bit = (pf >= lo && pf < lo + 32) ? (1u << (pf - lo)) : 0u;
-            fm[w] = code.info_mask[w] & (below | bit);
-            fv[w] = (u_ref[w] & below) | (~u_ref[w] & bit);
-            if (valid && jf >= lo && jf < lo + 32) tried[w] |= 1u << (jf - lo);      // tried set is indexed by info index
+            fm[w] = fresh ? 0u : (code.info_mask[w] & (below | bit));
+            fv[w] = fresh ? 0u : ((u_ref[w] & below) | (~u_ref[w] & bit));
+            if (valid && !fresh && jf >= lo && jf < lo + 32) tried[w] |= 1u << (jf - lo);      // tried set is indexed by info index
         }
-        if (valid) n_tried += 1;
-        if (leader && valid && a.tried) a.tried[(my_frame - a.frame_begin) * (long long)a.R + (n_tried - 1)] = jf;
+        if (valid && !fresh) n_tried += 1;
+        if (leader && valid && !fresh && a.tried) a.tried[(my_frame - a.frame_begin) * (long long)a.R + (n_tried - 1)] = jf;
         uint32_t flags = 0;
         PathT p;
         S::DecF::init(p, lane, valid);
