@@ -290,10 +290,22 @@ struct ListDecoder {
                         keys[lane] = make_uint4(l0, h0, l1, h1);
                         __syncwarp();
                         const double d0 = __hiloint2double((int)h0, (int)l0), d1 = __hiloint2double((int)h1, (int)l1);
+                        // rank of a candidate = number of smaller keys among the group's 2 MP: its sibling (in registers)
+                        // and the pairs of the MP - 1 other lanes (lane slot ^ j, one LDS.128 each)
                         uint32_t rank0 = 0, rank1 = 0;
+#ifndef PB_RANK_SELF
+#define PB_RANK_SELF 1
+#endif
+#if PB_RANK_SELF
+                        inc_if_lt(rank0, d1, d0); inc_if_lt(rank1, d0, d1);
+#pragma unroll
+                        for (int j = 1; j < MP; ++j) {
+                            const uint4 o = keys[lane ^ j];
+#else
 #pragma unroll
                         for (int j = 0; j < MP; ++j) {
                             const uint4 o = keys[gbase + j];
+#endif
                             const double ox = __hiloint2double((int)o.y, (int)o.x), oy = __hiloint2double((int)o.w, (int)o.z);
                             inc_if_lt(rank0, ox, d0); inc_if_lt(rank0, oy, d0);
                             inc_if_lt(rank1, ox, d1); inc_if_lt(rank1, oy, d1);

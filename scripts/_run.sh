@@ -1,4 +1,4 @@
-for cfg in "4 4.0 1048576" "8 4.0 1048576" "4 5.0 2097152" "8 5.0 2097152" "4 6.0 2097152"; do
-  for r in 1 0 1 0; do PB200_DL_REPLAY=$r python scripts/dl_stats.py $cfg | cut -c1-90 | sed "s/^/replay=$r /"; done
-  PB200_DL_BINNED=0 python scripts/dl_stats.py $cfg | cut -c1-90 | sed "s/^/old      /"
-done
+python scripts/ab_probe.py self1 --parity 20000 2>&1 | tail -9
+PB200_LIBRARY=ab/rs0.so python scripts/ab_probe.py self0 2>&1 | tail -1
+python scripts/ab_probe.py self1 2>&1 | tail -1
+PB200_LIBRARY=ab/rs0.so python scripts/ab_probe.py self0 2>&1 | tail -1
