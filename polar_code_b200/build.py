@@ -55,11 +55,14 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("nvcc not found: libpolar_b200.so must be built on a box with the CUDA toolkit")
     obj_dir = _OBJ if not _EXTRA else _CSRC / ("obj_" + "_".join(x.strip("-").replace("=", "") for x in _EXTRA))
     obj_dir.mkdir(exist_ok=True)
-    hdr_time = max(h.stat().st_mtime for h in _headers())
+    # *.inl files and the public header are included by the *_abi.cu units only; the kernel units depend on *.cuh / *.h
+    inl_time = max(h.stat().st_mtime for h in _headers())
+    hdr_time = max(h.stat().st_mtime for h in _headers() if h.suffix in (".cuh", ".h") and h.name != "polar_b200.h")
 
     def compile_one(src: Path) -> Path:
         obj = obj_dir / (src.stem + ".o")
-        if not force and obj.exists() and obj.stat().st_mtime > max(src.stat().st_mtime, hdr_time):
+        dep_time = inl_time if src.stem.endswith("_abi") else hdr_time
+        if not force and obj.exists() and obj.stat().st_mtime > max(src.stat().st_mtime, dep_time):
             return obj
         cmd = [nvcc, *NVCC_FLAGS, *_EXTRA, "-c", "-o", str(obj), str(src)]
         if verbose:

@@ -143,6 +143,8 @@ struct pb200_engine {
     unsigned int* d_bin_ctrl = nullptr;   // cursor, finished count, ring heads and tails
     int bin_ctrl_n = 0;
     int dl_binned = -1;                   // -1: not read yet (PB200_DL_BINNED, default 1)
+    std::map<int, KernelCfg> dl_cfg;      // launch configuration of the binned retry kernel per MP
+    long long dl_piece_max = 0;           // frames per DL-SCL piece, sized against free memory at the first DL-SCL sweep
     double* d_beta64 = nullptr;           // the caller's beta widened to fp64 for the current call [K,K]
     // per-warp global scratch of the decode kernels, one buffer per stream: kernels of one engine that are
     // enqueued on different streams may overlap on the device and must not share tree rows

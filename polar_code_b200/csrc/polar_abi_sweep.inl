@@ -153,16 +153,21 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
             // The warps of a CTA run in lock step behind one scheduler warp, so the CTA's serial section (claim, ring slots,
             // queue entries, LLR rows) idles all of them at once: split the resident warps over several CTAs per SM so that
             // one CTA's serial section overlaps another's decode (PB200_DL_WPC overrides the warps per CTA).
-            int want_wpc = std::max(4, kr.wpc / 2);
-            if (const char* env = getenv("PB200_DL_WPC")) want_wpc = std::max(1, std::min(32, atoi(env)));
-            if (want_wpc < kr.wpc) {
-                const size_t wb = warp_bytes(MP, code.N, code.K, true, code.K) + acc_bytes(MP);
-                int blocks = 0;
-                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, round, want_wpc * 32, wb * want_wpc) == cudaSuccess &&
-                    blocks * want_wpc >= kr.wpc * kr.ctas_per_sm) {
-                    kr.wpc = want_wpc; kr.ctas_per_sm = blocks; kr.smem = (int)(wb * want_wpc);
-                } else cudaGetLastError();
+            auto it = e->dl_cfg.find(MP);
+            if (it == e->dl_cfg.end()) {
+                int want_wpc = std::max(4, kr.wpc / 2);
+                if (const char* env = getenv("PB200_DL_WPC")) want_wpc = std::max(1, std::min(32, atoi(env)));
+                if (want_wpc < kr.wpc) {
+                    const size_t wb = warp_bytes(MP, code.N, code.K, true, code.K) + acc_bytes(MP);
+                    int blocks = 0;
+                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, round, want_wpc * 32, wb * want_wpc) == cudaSuccess &&
+                        blocks * want_wpc >= kr.wpc * kr.ctas_per_sm) {
+                        kr.wpc = want_wpc; kr.ctas_per_sm = blocks; kr.smem = (int)(wb * want_wpc);
+                    } else cudaGetLastError();
+                }
+                it = e->dl_cfg.emplace(MP, kr).first;
             }
+            kr = it->second;
         }
         rgrid = std::max(1, e->sms * kr.ctas_per_sm);
     }
@@ -175,12 +180,18 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
     // with another workload) -- the sweep then runs in more pieces instead of failing in cudaMalloc.
     long long piece_max = 1ll << 22;
     if (a.retries > 0) {
-        const size_t per_frame = (size_t)code.N * 4 + (size_t)code.K * 4 + entry_bytes(e);
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
-        const size_t have = free_b + e->llr_store_bytes + e->abs_store_bytes + e->q_bytes;    // what we hold already counts
-        while (piece_max < (1ll << 24) && (size_t)(piece_max * 2) * per_frame * 4 <= have) piece_max *= 2;
-        while (piece_max > (1ll << 16) && (size_t)piece_max * per_frame * 2 > have) piece_max /= 2;
+        // (decided once per engine: cudaMemGetInfo is a synchronous driver call that can take milliseconds on a busy
+        //  host, and it would sit in front of every sweep's first launch)
+        if (e->dl_piece_max == 0) {
+            const size_t per_frame = (size_t)code.N * 4 + (size_t)code.K * 4 + entry_bytes(e);
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
+            const size_t have = free_b + e->llr_store_bytes + e->abs_store_bytes + e->q_bytes;    // what we hold already counts
+            while (piece_max < (1ll << 24) && (size_t)(piece_max * 2) * per_frame * 4 <= have) piece_max *= 2;
+            while (piece_max > (1ll << 16) && (size_t)piece_max * per_frame * 2 > have) piece_max /= 2;
+            e->dl_piece_max = piece_max;
+        }
+        piece_max = e->dl_piece_max;
     }
     const long long total = a.n_frames, begin0 = a.frame_begin;
     const long long out_base = a.frame_begin;   // per-frame outputs are indexed by frame - frame_begin of the whole call
