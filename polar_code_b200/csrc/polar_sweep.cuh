@@ -861,13 +861,17 @@ __global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_bin_kerne
         if (me && lane == first) atomicAdd(ring_fill(jn), __popc(peers));         // (a claim that overtakes the slot write waits on the slot)
     };
 
-    // Scheduler: ONE warp per CTA talks to the rings and claims work for the whole CTA (FPW frames per warp), the other
-    // warps wait at a barrier -- 148 pollers instead of 4 736, two atomics per CTA step on the ring's own cache line,
-    // and the warps of a CTA decode the same ring in lock step (same start phase, same instruction stream).
+    // Scheduler: ONE warp per CTA and step talks to the rings and claims work for the whole CTA (FPW frames per warp), the
+    // other warps wait at a barrier -- 148-296 pollers instead of 4 736, two atomics per CTA step on the ring's own cache
+    // line, and the warps of a CTA decode the same ring in lock step (same start phase, same instruction stream).  The
+    // scheduler of a step is the warp that finishes the previous step FIRST, so its claim (a few L2 round trips) runs
+    // while the slower warps are still pushing.
     // Fast path: keep popping the ring popped last, so rings are drained one after the other and the frames advance level
     // by level.  Slow path, when that ring runs dry: read the cursor, the finished count and every ring's fill count,
     // then leave / admit new frames / pick the fullest ring (or, when no ring holds FPW frames, the highest rings) / wait.
     __shared__ int s_cmd;                     // 0 decode, 1 admit, 2 leave
+    __shared__ unsigned int s_arrive;         // warps that finished the previous step
+    __shared__ int s_sticky;                  // ring popped last
     __shared__ unsigned int s_base;           // admission: first queue entry of this CTA step
     __shared__ int s_plan[1024];              // ring of each frame slot of the CTA (-1 none)
     __shared__ unsigned int s_pos[1024];      // claimed ring position
@@ -877,7 +881,8 @@ __global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_bin_kerne
     unsigned long long st_sched_ns = 0, t_kernel0 = 0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_kernel0));
     unsigned int backoff = 500u;
-    int sticky = -1;                          // (scheduler warp only)
+    if (threadIdx.x == 0) { s_arrive = 0; s_sticky = -1; }
+    __syncthreads();
     for (;;) {
         bool push_go = false;                 // what the common tail of the iteration pushes (one call site)
         long long push_idx = -1;
@@ -885,9 +890,13 @@ __global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_bin_kerne
         uint32_t tried[XW];
 #pragma unroll
         for (int k = 0; k < XW; ++k) tried[k] = 0;
-        if (warp == 0) {
+        unsigned int arrived = 0;
+        if (lane == 0) arrived = atomicAdd(&s_arrive, 1u);
+        const bool i_schedule = __shfl_sync(kFull, arrived, 0) == 0;
+        if (i_schedule) {
             int cmd = 0;
             unsigned int base = 0;
+            int sticky = s_sticky;
             unsigned long long t_sched0 = 0;
             if (lane == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_sched0));
             // claim up to CTA_F frames of ring b; fills the CTA plan; returns the number got
@@ -985,7 +994,7 @@ __global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_bin_kerne
                 backoff = backoff < 8000u ? backoff * 2u : backoff;
             }
             backoff = 500u;
-            if (lane == 0) { s_cmd = cmd; s_base = base; }
+            if (lane == 0) { s_cmd = cmd; s_base = base; s_sticky = sticky; }
             if (lane == 0) {                                                  // statistics: time this CTA's scheduler spent
                 unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
                 st_sched_ns += t1 - t_sched0;
@@ -999,6 +1008,7 @@ __global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_bin_kerne
         bool valid = cmd == 0 && s_ok[myi] != 0;
         const unsigned int mypos = s_pos[myi];
         const unsigned int adm_base = s_base;
+        if (i_schedule && lane == 0) s_arrive = 0;                            // (every warp of the CTA has arrived: it is past the barrier)
         __syncthreads();                                                      // the plan may be rewritten from here on
         // Admission (cmd 1): the baseline pass queued these frames WITHOUT a trace (tracing every frame costs a quarter of
         // the baseline pass, and most frames never need it).  Their first |L0| row comes from replaying the baseline
@@ -1129,10 +1139,10 @@ __global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_bin_kerne
         push_next(push_go, push_idx, tried, push_flags);
         __syncwarp();
     }
-    if (warp == 0 && lane == 0) {
+    if (lane == 0) {
         unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        atomicMax(&stats[6], (unsigned int)(st_sched_ns >> 10));              // longest scheduler time of a CTA (~us)
-        atomicMax(&stats[7], (unsigned int)((t1 - t_kernel0) >> 10));         // longest CTA lifetime (~us)
+        atomicMax(&stats[6], (unsigned int)(st_sched_ns >> 10));              // longest time a warp spent scheduling (~us)
+        atomicMax(&stats[7], (unsigned int)((t1 - t_kernel0) >> 10));         // longest warp lifetime (~us)
     }
     if (lane == 0 && st_batches) {
         atomicAdd(&stats[2], st_batches); atomicAdd(&stats[3], st_decodes); atomicAdd(&stats[4], st_phi); atomicAdd(&stats[5], st_mixed);

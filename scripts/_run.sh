@@ -1,4 +1,4 @@
-python scripts/ab_probe.py self1 --parity 20000 2>&1 | tail -9
-PB200_LIBRARY=ab/rs0.so python scripts/ab_probe.py self0 2>&1 | tail -1
-python scripts/ab_probe.py self1 2>&1 | tail -1
-PB200_LIBRARY=ab/rs0.so python scripts/ab_probe.py self0 2>&1 | tail -1
+python scripts/_probe_nobeta.py
+python scripts/dl_stats.py 4 4.0 1048576 | cut -c1-330
+python scripts/dl_stats.py 8 4.0 1048576 | cut -c1-330
+timeout 900 python -m pytest tests -x -q -m gpu -k "dl or sweep or published or parity" 2>&1 | tail -2
