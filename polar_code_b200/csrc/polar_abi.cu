@@ -415,17 +415,23 @@ static void pin_scratch_in_l2(pb200_engine* e, cudaStream_t st, unsigned char* s
     }
     if (e->l2_window_max == -2 || e->device < 0 || e->device >= 64) return;
     if (!enable) {
-        auto it = e->l2_window.find(st);
-        if (it == e->l2_window.end() || it->second.first == nullptr) return;
-        cudaStreamAttrValue v{};
-        v.accessPolicyWindow.base_ptr = nullptr;
-        v.accessPolicyWindow.num_bytes = 0;
-        v.accessPolicyWindow.hitRatio = 0.f;
-        v.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
-        v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-        if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
-        it->second = {nullptr, 0};
-        l2_release_window(e->device);
+        // A thread-per-frame launch wants the whole L2: clear the windows of ALL streams of this engine (the host-buffer
+        // path leaves one on each of its three internal streams), not only this stream's -- as long as one of them holds
+        // the set-aside, SC / M = 1 run at 0.67e9 instead of 1.6e9 frames/s.  The next list launch on a stream sets its
+        // window again.
+        (void)st;
+        for (auto& kv : e->l2_window) {
+            if (kv.second.first == nullptr) continue;
+            cudaStreamAttrValue v{};
+            v.accessPolicyWindow.base_ptr = nullptr;
+            v.accessPolicyWindow.num_bytes = 0;
+            v.accessPolicyWindow.hitRatio = 0.f;
+            v.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+            v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+            if (cudaStreamSetAttribute(kv.first, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
+            kv.second = {nullptr, 0};
+            l2_release_window(e->device);
+        }
         return;
     }
     auto& cur = e->l2_window[st];
