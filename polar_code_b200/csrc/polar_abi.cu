@@ -144,6 +144,11 @@ struct pb200_engine {
     int bin_ctrl_n = 0;
     int dl_binned = -1;                   // -1: not read yet (PB200_DL_BINNED, default 1)
     std::map<int, KernelCfg> dl_cfg;      // launch configuration of the binned retry kernel per MP
+    // fraction of frames the previous DL-SCL piece queued for retries (read back asynchronously): picks the admission mode
+    unsigned int* h_queued = nullptr;     // pinned: [0] queued frames of the last piece
+    cudaEvent_t queued_ev = nullptr;
+    long long queued_of = 0;              // frames of that piece (0: nothing in flight / known)
+    double dl_fail_frac = -1.0;           // last known failure fraction (-1: unknown)
     long long dl_piece_max = 0;           // frames per DL-SCL piece, sized against free memory at the first DL-SCL sweep
     double* d_beta64 = nullptr;           // the caller's beta widened to fp64 for the current call [K,K]
     // per-warp global scratch of the decode kernels, one buffer per stream: kernels of one engine that are
@@ -270,6 +275,8 @@ extern "C" void pb200_destroy(pb200_engine* e) {
     cudaFree(e->d_info_pos); cudaFree(e->d_info_mask); cudaFree(e->d_crc_tab); cudaFree(e->d_rm_src); cudaFree(e->d_rm_cnt); cudaFree(e->d_tx_src);
     for (auto& kv : e->enc_tabs) cudaFree(kv.second);
     cudaFree(e->d_bin_ring); cudaFree(e->d_bin_ctrl);
+    if (e->h_queued) cudaFreeHost(e->h_queued);
+    if (e->queued_ev) cudaEventDestroy(e->queued_ev);
     cudaFree(e->d_llr_store); cudaFree(e->d_abs_store); cudaFree(e->d_rm_dst); cudaFree(e->d_beta64);
     for (auto& kv : e->scratch) cudaFree(kv.second.first); cudaFree(e->d_q[0]); cudaFree(e->d_q[1]); cudaFree(e->d_q_counts);
     for (int i = 0; i < 3; ++i) {

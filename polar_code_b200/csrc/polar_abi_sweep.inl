@@ -136,7 +136,15 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
     // Frame-per-group retry kernel: the baseline pass records the leaf-LLR trace and writes |L0| of every queued frame
     // (kind 2).  Binned retry kernel: the baseline pass is the plain one -- queued frames get their first |L0| row from an
     // "attempt 0" replay inside the retry kernel, so the frames that pass (most of them) never pay for a trace.
-    bool replay = binned;
+    // Which admission is faster depends on how many frames fail: tracing every frame costs 0.9 ms per Mi frames, replaying
+    // the queued ones a decode each -- break-even near 12 % failures (B200, M = 4).  Both give identical results
+    // (tests/test_gpu_dlbin.py), so the choice follows the failure fraction of this engine's previous DL-SCL piece, read
+    // back asynchronously (unknown: replay, the better one over most of a FER curve).  PB200_DL_REPLAY=0/1 pins it.
+    if (binned && e->queued_of > 0 && e->queued_ev && cudaEventQuery(e->queued_ev) == cudaSuccess) {
+        e->dl_fail_frac = (double)e->h_queued[0] / (double)e->queued_of;
+        e->queued_of = 0;
+    }
+    bool replay = binned && !(e->dl_fail_frac > 0.12);
     if (const char* env = getenv("PB200_DL_REPLAY")) replay = binned && env[0] != '0';
     const bool trace = a.retries > 0 && !replay;
     auto pick = [&](int kind) { return big ? pb_sweep_kernel_9(MP, kind) : code.n == 7 ? pb_sweep_kernel_7s(MP, kind) : pb_sweep_kernel_7(MP, kind); };
@@ -287,6 +295,13 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
             }
             void* args[3] = {(void*)&code, (void*)&e->tb, (void*)&q};
             CUDA_TRY(cudaLaunchKernel(round, dim3(rgrid), dim3(kr.wpc * 32), args, kr.smem, st));
+            if (binned && e->queued_of == 0) {            // (one read-back in flight at a time)
+                if (!e->h_queued) CUDA_TRY(cudaMallocHost((void**)&e->h_queued, sizeof(unsigned int)));
+                if (!e->queued_ev) CUDA_TRY(cudaEventCreateWithFlags(&e->queued_ev, cudaEventDisableTiming));
+                CUDA_TRY(cudaMemcpyAsync(e->h_queued, e->d_q_counts, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaEventRecord(e->queued_ev, st));
+                e->queued_of = nf;
+            }
         }
     }
     return PB200_OK;

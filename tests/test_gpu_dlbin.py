@@ -124,17 +124,37 @@ def test_sweep_counters_equal_full_redecode(engines, g128):
     assert abs(int(a[3]) - int(b[3])) <= 2 and abs(int(a[7]) - int(b[7])) <= 16   # DL frame errors, retries (near-tie frames)
 
 
-def test_scheduler_statistics(engines, g128):
-    """pb200_debug_bin_stats: every retry decode is counted once, batches are (almost) full, decodes start late."""
+def test_scheduler_statistics(engines, g128, monkeypatch):
+    """pb200_debug_bin_stats: every retry decode is counted once (plus one attempt-0 replay per queued frame when the
+    baseline pass ran without the trace), batches are (almost) full, decodes start late."""
     import ctypes as C
     eb, _ = engines
     beta = torch.as_tensor(g128["beta_M4"], device="cuda")
-    c = torch.zeros(16, dtype=torch.int64, device="cuda")
-    eb.sweep(c, M=4, noise_var=_nv(4.0), n_frames=400000, seed=2, stream_id=3, k_payload=40, retries=8, beta=beta)
-    st = (C.c_uint * 8)()
-    assert eb.lib.pb200_debug_bin_stats(eb._h, st) == 0
-    cc = c.cpu().numpy()
-    queued = int(cc[1])                                  # frames whose baseline decode failed the CRC
-    assert st[3] == int(cc[7]) + queued                  # retry decodes + one attempt-0 replay per queued frame
-    assert st[3] / st[2] > 6.5                           # frames per batch (of 8)
-    assert st[4] / st[2] > 40                            # mean start phase of a batch
+    for replay in ("1", "0"):
+        monkeypatch.setenv("PB200_DL_REPLAY", replay)      # (unpinned, the engine picks the mode from its last failure fraction)
+        c = torch.zeros(16, dtype=torch.int64, device="cuda")
+        eb.sweep(c, M=4, noise_var=_nv(4.0), n_frames=400000, seed=2, stream_id=3, k_payload=40, retries=8, beta=beta)
+        st = (C.c_uint * 8)()
+        assert eb.lib.pb200_debug_bin_stats(eb._h, st) == 0
+        cc = c.cpu().numpy()
+        queued = int(cc[1])                                  # frames whose baseline decode failed the CRC
+        assert st[3] == int(cc[7]) + (queued if replay == "1" else 0)
+        assert st[3] / st[2] > 6.5                           # frames per batch (of 8)
+        assert st[4] / st[2] > 40                            # mean start phase of a batch
+
+
+def test_adaptive_admission_is_invisible(engines, g128, monkeypatch):
+    """Unpinned, the engine switches the admission mode on the failure fraction of its previous DL-SCL piece (> 12 %: traced
+    baseline, else replay).  Whatever it picks, the counters are those of the pinned modes."""
+    eb, _ = engines
+    monkeypatch.delenv("PB200_DL_REPLAY", raising=False)
+    beta = torch.as_tensor(g128["beta_M4"], device="cuda")
+    res = {}
+    for snr in (3.0, 6.0, 3.0, 6.0, 6.0):                    # alternating: every call sees the other regime's history
+        c = torch.zeros(16, dtype=torch.int64, device="cuda")
+        eb.sweep(c, M=4, noise_var=_nv(snr), n_frames=100000, seed=9, stream_id=3, k_payload=40, retries=8, beta=beta)
+        torch.cuda.synchronize()
+        res.setdefault(snr, []).append(c.cpu().numpy())
+    for snr, rs in res.items():
+        for r in rs[1:]:
+            assert np.array_equal(rs[0], r), snr
