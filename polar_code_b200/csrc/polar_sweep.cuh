@@ -832,11 +832,8 @@ __global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_bin_kerne
     auto ring_tail = [&](int b) { return a.bin_ctrl + 96 + (size_t)b * 32 + 1; };
     auto ring_fill = [&](int b) { return reinterpret_cast<int*>(a.bin_ctrl + 96 + (size_t)b * 32 + 2); };
     const unsigned int cap_mask = a.bin_cap - 1;
-    // per-warp scratch of the scheduler in the (dead between decodes) tree rows: ring fill counts, the batch plan
+    // scratch of the scheduling warp in its (dead between decodes) tree rows: the ring fill counts
     unsigned int* cnt = reinterpret_cast<unsigned int*>(wm.ts);              // [K]
-    int* plan = reinterpret_cast<int*>(wm.xchg);                             // [FPW] ring of each group (-1 none)
-    unsigned int* ppos = reinterpret_cast<unsigned int*>(wm.xchg) + 32;      // [FPW] claimed ring position
-    int* pok = reinterpret_cast<int*>(wm.xchg) + 64;                         // [FPW] position valid
     Entry* const entries = reinterpret_cast<Entry*>(a.q_in);
 
     // score the next flip of this group's frame from ab[] and queue it (group-uniform arguments).  The leaders of a warp
@@ -1037,103 +1034,103 @@ __global__ void __launch_bounds__(MP >= 4 ? PB_RETRY_THREADS : 512) dl_bin_kerne
             eidx = v;                                                         // the entry / |L0| loads below depend on it and read L2 (ld.cg)
         }
         if (__any_sync(kFull, valid)) {
-        if (!fresh) eidx = __shfl_sync(kFull, eidx, gbase);
-        __syncwarp();
+            if (!fresh) eidx = __shfl_sync(kFull, eidx, gbase);
+            __syncwarp();
 
-        // ---- the frames of this batch ----------------------------------------------------------------------
-        long long my_frame = -1, store = 0;
-        uint32_t eflags = 0, n_tried = 0;
-        uint32_t u_ref[XW], u_sent[XW];
+            // ---- the frames of this batch ----------------------------------------------------------------------
+            long long my_frame = -1, store = 0;
+            uint32_t eflags = 0, n_tried = 0;
+            uint32_t u_ref[XW], u_sent[XW];
 #pragma unroll
-        for (int k = 0; k < XW; ++k) { u_ref[k] = 0; u_sent[k] = 0; }
-        if (valid) {
-            unsigned long long w[EW];
-            const unsigned long long* ep = reinterpret_cast<const unsigned long long*>(entries + eidx);
-#pragma unroll
-            for (int k = 0; k < EW; ++k) w[k] = __ldcg(ep + k);
-            Entry e;
-            memcpy(&e, w, sizeof(Entry));
-            my_frame = e.h.frame; eflags = e.h.flags; n_tried = e.h.n_tried; store = e.store;
-#pragma unroll
-            for (int k = 0; k < XW; ++k) { u_ref[k] = e.u[k]; tried[k] = e.tried[k]; u_sent[k] = e.u_sent[k]; }
-        }
-        {
-            const float* row = nullptr;
-            // (sweep mode: the LLR-store row of a frame is its queue slot, so the row loads do not wait for the entry)
-            if (valid) row = (a.llr == nullptr) ? a.llr_store + eidx * (long long)code.N
-                                                : a.llr + (my_frame - a.frame_begin) * (long long)a.in_len;
-            load_channel_ids<MP, WM, true>(code, tb, wm, row, lane);
-        }
-        const float* chanf = wm.chan + fme;
-        const int jf = (valid && !fresh) ? myb : 0;                           // the ring IS the index to flip
-        const int pf = fresh ? 0 : (int)__ldg(&tb.info_pos[jf]);
-        // start of the warp's decode: the lowest flipped phase of the batch, rounded down to a phase pair
-        int pmin = valid ? pf : code.N;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) pmin = min(pmin, __shfl_xor_sync(kFull, pmin, o));
-        const int phi_start = pmin & ~1;
-        {   // statistics of this warp (flushed once, at the end)
-            const uint32_t vm = __ballot_sync(kFull, valid && leader);
-            const uint32_t same = __ballot_sync(kFull, !valid || pf == pmin);
-            st_batches += 1; st_decodes += __popc(vm); st_phi += (unsigned int)phi_start; st_mixed += same != kFull ? 1u : 0u;
-        }
-        int jstart = 0;
-#pragma unroll
-        for (int w = 0; w < XW; ++w) {
-            const int lo = w * 32;
-            const uint32_t below = (phi_start >= lo + 32) ? 0xffffffffu : (phi_start <= lo ? 0u : ((1u << (phi_start - lo)) - 1u));
-            jstart += __popc(code.info_mask[w] & below);
-        }
-        // _force_vector (flip.py:30-34): prefix of the reference bits, then the flipped bit, rest free
-        uint32_t fm[XW], fv[XW];
-#pragma unroll
-        for (int w = 0; w < XW; ++w) {
-            const int lo = w * 32;
-            const uint32_t below = (pf >= lo + 32) ? 0xffffffffu : (pf <= lo ? 0u : ((1u << (pf - lo)) - 1u));
-            const uint32_t bit = (pf >= lo && pf < lo + 32) ? (1u << (pf - lo)) : 0u;
-            fm[w] = fresh ? 0u : (code.info_mask[w] & (below | bit));
-            fv[w] = fresh ? 0u : ((u_ref[w] & below) | (~u_ref[w] & bit));
-            if (valid && !fresh && jf >= lo && jf < lo + 32) tried[w] |= 1u << (jf - lo);      // tried set is indexed by info index
-        }
-        if (valid && !fresh) n_tried += 1;
-        if (leader && valid && !fresh && a.tried) a.tried[(my_frame - a.frame_begin) * (long long)a.R + (n_tried - 1)] = jf;
-        uint32_t flags = 0;
-        PathT p;
-        S::DecF::init(p, lane, valid);
-        S::DecF::template run<true, true>(code, tb.info_mask, wm, p, lane, chanf, fm, fv, flags, phi_start, jstart, pf & ~1);   // retry_with_flip (flip.py:37-62)
-        typename S::Best b;
-        S::pick_best(code, tb, p, lane, flags | eflags, b);
-        bool more = false;
-        if (valid) {
-            if (leader) acc[cNearTie] += ((b.flags & PB_FLAG_NEAR_TIE) && !(eflags & PB_FLAG_NEAR_TIE)) ? 1u : 0u;
-            const bool pass = code.crc_deg == 0 ? true : b.pass;
-            more = !(pass || (int)n_tried >= a.retries || (int)n_tried >= K);          // flip.py:111,134
-            if (!more && leader) S::finish_dl(code, tb, a, wm, lane, my_frame, b, n_tried, u_sent, acc);
-        }
-        {
-            const uint32_t fmask_done = __ballot_sync(kFull, valid && !more && leader);
-            if (lane == 0 && fmask_done) atomicAdd(done, (unsigned int)__popc(fmask_done));
-        }
-        __syncwarp();
-        if (more) {
-            // the next attempt starts from THIS attempt's best path (flip.py:127-133): new entry, new |L0| rows >= jstart
-            if (leader) {
-                Entry e;
-                e.h.frame = my_frame; e.h.flags = b.flags; e.h.n_tried = n_tried;
-#pragma unroll
-                for (int k = 0; k < XW; ++k) { e.u[k] = b.u[k]; e.tried[k] = tried[k]; e.u_sent[k] = u_sent[k]; }
-                e.store = (uint32_t)store; e.pad = 0;
+            for (int k = 0; k < XW; ++k) { u_ref[k] = 0; u_sent[k] = 0; }
+            if (valid) {
                 unsigned long long w[EW];
-                memcpy(w, &e, sizeof(Entry));
-                unsigned long long* ep = reinterpret_cast<unsigned long long*>(entries + eidx);
+                const unsigned long long* ep = reinterpret_cast<const unsigned long long*>(entries + eidx);
 #pragma unroll
-                for (int k = 0; k < EW; ++k) ep[k] = w[k];
+                for (int k = 0; k < EW; ++k) w[k] = __ldcg(ep + k);
+                Entry e;
+                memcpy(&e, w, sizeof(Entry));
+                my_frame = e.h.frame; eflags = e.h.flags; n_tried = e.h.n_tried; store = e.store;
+#pragma unroll
+                for (int k = 0; k < XW; ++k) { u_ref[k] = e.u[k]; tried[k] = e.tried[k]; u_sent[k] = e.u_sent[k]; }
             }
-            float* dst = a.abs_store + eidx * (long long)K;
-            S::DecF::trace_walk(code, wm, lane, b.lane, [&](int j, float L) { const float v = fabsf(L); ab[j] = v; dst[j] = v; }, jstart);   // flip.py:133
-            for (int j = slot; j < jstart; j += MP) ab[j] = __ldcg(dst + j);          // prefix rows: traced by earlier attempts
-        }
-        push_go = more; push_idx = eidx; push_flags = b.flags;
+            {
+                const float* row = nullptr;
+                // (sweep mode: the LLR-store row of a frame is its queue slot, so the row loads do not wait for the entry)
+                if (valid) row = (a.llr == nullptr) ? a.llr_store + eidx * (long long)code.N
+                                                    : a.llr + (my_frame - a.frame_begin) * (long long)a.in_len;
+                load_channel_ids<MP, WM, true>(code, tb, wm, row, lane);
+            }
+            const float* chanf = wm.chan + fme;
+            const int jf = (valid && !fresh) ? myb : 0;                           // the ring IS the index to flip
+            const int pf = fresh ? 0 : (int)__ldg(&tb.info_pos[jf]);
+            // start of the warp's decode: the lowest flipped phase of the batch, rounded down to a phase pair
+            int pmin = valid ? pf : code.N;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) pmin = min(pmin, __shfl_xor_sync(kFull, pmin, o));
+            const int phi_start = pmin & ~1;
+            {   // statistics of this warp (flushed once, at the end)
+                const uint32_t vm = __ballot_sync(kFull, valid && leader);
+                const uint32_t same = __ballot_sync(kFull, !valid || pf == pmin);
+                st_batches += 1; st_decodes += __popc(vm); st_phi += (unsigned int)phi_start; st_mixed += same != kFull ? 1u : 0u;
+            }
+            int jstart = 0;
+#pragma unroll
+            for (int w = 0; w < XW; ++w) {
+                const int lo = w * 32;
+                const uint32_t below = (phi_start >= lo + 32) ? 0xffffffffu : (phi_start <= lo ? 0u : ((1u << (phi_start - lo)) - 1u));
+                jstart += __popc(code.info_mask[w] & below);
+            }
+            // _force_vector (flip.py:30-34): prefix of the reference bits, then the flipped bit, rest free
+            uint32_t fm[XW], fv[XW];
+#pragma unroll
+            for (int w = 0; w < XW; ++w) {
+                const int lo = w * 32;
+                const uint32_t below = (pf >= lo + 32) ? 0xffffffffu : (pf <= lo ? 0u : ((1u << (pf - lo)) - 1u));
+                const uint32_t bit = (pf >= lo && pf < lo + 32) ? (1u << (pf - lo)) : 0u;
+                fm[w] = fresh ? 0u : (code.info_mask[w] & (below | bit));
+                fv[w] = fresh ? 0u : ((u_ref[w] & below) | (~u_ref[w] & bit));
+                if (valid && !fresh && jf >= lo && jf < lo + 32) tried[w] |= 1u << (jf - lo);      // tried set is indexed by info index
+            }
+            if (valid && !fresh) n_tried += 1;
+            if (leader && valid && !fresh && a.tried) a.tried[(my_frame - a.frame_begin) * (long long)a.R + (n_tried - 1)] = jf;
+            uint32_t flags = 0;
+            PathT p;
+            S::DecF::init(p, lane, valid);
+            S::DecF::template run<true, true>(code, tb.info_mask, wm, p, lane, chanf, fm, fv, flags, phi_start, jstart, pf & ~1);   // retry_with_flip (flip.py:37-62)
+            typename S::Best b;
+            S::pick_best(code, tb, p, lane, flags | eflags, b);
+            bool more = false;
+            if (valid) {
+                if (leader) acc[cNearTie] += ((b.flags & PB_FLAG_NEAR_TIE) && !(eflags & PB_FLAG_NEAR_TIE)) ? 1u : 0u;
+                const bool pass = code.crc_deg == 0 ? true : b.pass;
+                more = !(pass || (int)n_tried >= a.retries || (int)n_tried >= K);          // flip.py:111,134
+                if (!more && leader) S::finish_dl(code, tb, a, wm, lane, my_frame, b, n_tried, u_sent, acc);
+            }
+            {
+                const uint32_t fmask_done = __ballot_sync(kFull, valid && !more && leader);
+                if (lane == 0 && fmask_done) atomicAdd(done, (unsigned int)__popc(fmask_done));
+            }
+            __syncwarp();
+            if (more) {
+                // the next attempt starts from THIS attempt's best path (flip.py:127-133): new entry, new |L0| rows >= jstart
+                if (leader) {
+                    Entry e;
+                    e.h.frame = my_frame; e.h.flags = b.flags; e.h.n_tried = n_tried;
+#pragma unroll
+                    for (int k = 0; k < XW; ++k) { e.u[k] = b.u[k]; e.tried[k] = tried[k]; e.u_sent[k] = u_sent[k]; }
+                    e.store = (uint32_t)store; e.pad = 0;
+                    unsigned long long w[EW];
+                    memcpy(w, &e, sizeof(Entry));
+                    unsigned long long* ep = reinterpret_cast<unsigned long long*>(entries + eidx);
+#pragma unroll
+                    for (int k = 0; k < EW; ++k) ep[k] = w[k];
+                }
+                float* dst = a.abs_store + eidx * (long long)K;
+                S::DecF::trace_walk(code, wm, lane, b.lane, [&](int j, float L) { const float v = fabsf(L); ab[j] = v; dst[j] = v; }, jstart);   // flip.py:133
+                for (int j = slot; j < jstart; j += MP) ab[j] = __ldcg(dst + j);          // prefix rows: traced by earlier attempts
+            }
+            push_go = more; push_idx = eidx; push_flags = b.flags;
         }   // (decode path)
         __syncwarp();
         push_next(push_go, push_idx, tried, push_flags);
