@@ -146,9 +146,18 @@ __global__ void __launch_bounds__(LOGMAX <= 7 ? (MP > 1 ? PB_LIST_THREADS : 1024
         const int64_t frame = frame0 + lane / MP;
         const bool valid = frame < a.B;
         if (tb.E == 0) {
-            if (frame0 + FPW <= a.B && (code.N & 31) == 0) stage_channel_block<MP>(wm, code.N, lane, a.llr + frame0 * (int64_t)code.N);
-            else stage_channel_rows<MP>(wm, code.N, lane, [&](int f) -> const float* {
-                return frame0 + f < a.B ? a.llr + (frame0 + f) * (int64_t)a.in_len : nullptr; });
+            // whole rows by 16-byte cp.async when the tile fits (N = 128, MP >= 4: one DRAM round trip per frame group),
+            // else 32 columns at a time
+#ifndef PB_DECODE_ASYNC_ROWS
+#define PB_DECODE_ASYNC_ROWS 1
+#endif
+            bool staged = false;
+            if (PB_DECODE_ASYNC_ROWS) staged = stage_channel_rows_async<MP>(wm, code.N, lane, valid ? a.llr + frame * (int64_t)a.in_len : nullptr);
+            if (!staged) {
+                if (frame0 + FPW <= a.B && (code.N & 31) == 0) stage_channel_block<MP>(wm, code.N, lane, a.llr + frame0 * (int64_t)code.N);
+                else stage_channel_rows<MP>(wm, code.N, lane, [&](int f) -> const float* {
+                    return frame0 + f < a.B ? a.llr + (frame0 + f) * (int64_t)a.in_len : nullptr; });
+            }
         } else load_channel<MP, WM>(code, tb, wm, a.llr, a.in_len, frame0, a.B, lane);
         const float* chanf = wm.chan + lane / MP;
         uint32_t flags = 0;

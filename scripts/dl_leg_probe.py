@@ -1,3 +1,4 @@
+"""DL-SCL sweep legs in bench.py order (beta / no beta, M = 4 / 8): per-call times, to spot host-side stalls between launches."""
 import sys, time
 sys.path.insert(0, ".")
 import numpy as np, torch
