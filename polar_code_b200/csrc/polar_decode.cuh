@@ -177,7 +177,11 @@ struct ListDecoder {
     // prefix adds the same constant to every path of the frame, and with the reset at my_start
     // the result does not depend on which other frames share the warp.  jstart = number of information phases below
     // phi_start (first trace row written).
-    template <bool TRACE = false, bool JUMP = false>
+    // UMASK: fetch the info-mask words from the kernel parameters (see the phase code) -- measured on B200: +3 % (M = 4) /
+    // +9 % (M = 8) for the plain list decode kernel, but -6 % for the thread-per-frame kernels and -13 % for the sweep /
+    // retry kernels (the by-value Code then lives in local memory next to their larger state), so only decode_kernel's
+    // plain list instantiations ask for it.
+    template <bool TRACE = false, bool JUMP = false, bool UMASK = false>
     static __device__ __forceinline__ void run(const Code& code, const uint32_t* __restrict__ imask, const WM& wm, PathT& p,
                                                int lane, const float* chanf, const uint32_t (&fmask)[XW],
                                                const uint32_t (&fval)[XW], uint32_t& flags, int phi_start = 0, int jstart = 0,
@@ -213,7 +217,13 @@ struct ListDecoder {
             // at the end of every phase)
             if (R <= 0 || R == 10) {
                 if ((phi & 31) == 0 && !(JUMP && warm)) {
-                    cur_info = __ldg(imask + (phi >> 5));     // (a dynamic index into the by-value Code would force it into local memory)
+                    if constexpr (UMASK) {
+                        // word phi/32 of the info mask from the kernel parameters instead of a global load
+                        uint32_t mw = 0;
+#pragma unroll
+                        for (int k = 0; k < XW; ++k) if (k == (phi >> 5)) mw = code.info_mask[k];
+                        cur_info = mw;
+                    } else cur_info = __ldg(imask + (phi >> 5));
                     if constexpr (FORCED) {
 #pragma unroll
                         for (int k = 0; k < XW; ++k) if (k == (phi >> 5)) { cur_fm = fmask[k]; cur_fv = fval[k]; }

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(LOGMAX <= 7 ? (MP > 1 ? PB_LIST_THREADS : 1024
         if constexpr (FORCED) load_force<XW>(code, a.force, frame, valid, fmask, fval, flags);
         PathT p;
         Dec::init(p, lane, valid);
-        Dec::template run<TRACE>(code, tb.info_mask, wm, p, lane, chanf, fmask, fval, flags);
+        Dec::template run<TRACE, false, (MP > 1 && !FORCED && !TRACE && METRIC)>(code, tb.info_mask, wm, p, lane, chanf, fmask, fval, flags);
 
         // u-hat = x-hat * F^{(x)n}
         uint32_t u[XW];
