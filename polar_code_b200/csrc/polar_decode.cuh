@@ -181,7 +181,7 @@ struct ListDecoder {
     // +9 % (M = 8) for the plain list decode kernel, but -6 % for the thread-per-frame kernels and -13 % for the sweep /
     // retry kernels (the by-value Code then lives in local memory next to their larger state), so only decode_kernel's
     // plain list instantiations ask for it.
-    template <bool TRACE = false, bool JUMP = false, bool UMASK = false>
+    template <bool TRACE = false, bool JUMP = false, int UMASK = 0>
     static __device__ __forceinline__ void run(const Code& code, const uint32_t* __restrict__ imask, const WM& wm, PathT& p,
                                                int lane, const float* chanf, const uint32_t (&fmask)[XW],
                                                const uint32_t (&fval)[XW], uint32_t& flags, int phi_start = 0, int jstart = 0,
@@ -217,11 +217,21 @@ struct ListDecoder {
             // at the end of every phase)
             if (R <= 0 || R == 10) {
                 if ((phi & 31) == 0 && !(JUMP && warm)) {
-                    if constexpr (UMASK) {
+                    if constexpr (UMASK == 1) {
                         // word phi/32 of the info mask from the kernel parameters instead of a global load
                         uint32_t mw = 0;
 #pragma unroll
                         for (int k = 0; k < XW; ++k) if (k == (phi >> 5)) mw = code.info_mask[k];
+                        cur_info = mw;
+                    } else if constexpr (UMASK == 2) {
+                        // the same with each word laundered through a register, so that the chain stays a chain of selects
+                        uint32_t mw = 0;
+#pragma unroll
+                        for (int k = 0; k < XW; ++k) {
+                            uint32_t wk;
+                            asm("mov.u32 %0, %1;" : "=r"(wk) : "r"(code.info_mask[k]));
+                            if (k == (phi >> 5)) mw = wk;
+                        }
                         cur_info = mw;
                     } else cur_info = __ldg(imask + (phi >> 5));
                     if constexpr (FORCED) {

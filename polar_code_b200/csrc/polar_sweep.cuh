@@ -597,7 +597,10 @@ __global__ void __launch_bounds__(PB_SWEEP_THREADS) sweep_kernel(const Code code
         PathT p;
         S::DecU::init(p, lane, valid);
         const float* chanf = wm.chan + lane / MP;
-        S::DecU::template run<TRACE>(code, tb.info_mask, wm, p, lane, chanf, fm, fv, flags);
+#ifndef PB_SWEEP_UMASK
+#define PB_SWEEP_UMASK 0
+#endif
+        S::DecU::template run<TRACE, false, (TRACE || MP == 1) ? 0 : PB_SWEEP_UMASK>(code, tb.info_mask, wm, p, lane, chanf, fm, fv, flags);
         typename S::Best b;
         S::pick_best(code, tb, p, lane, flags, b);
         bool need = false;
