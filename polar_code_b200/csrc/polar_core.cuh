@@ -441,11 +441,18 @@ struct Tree {
     //            height H-1, 2 of H-2 and 1 of H-3, so each level is stored once and never re-loaded (the tall rows
     //            live in the L2-resident scratch; re-reading them was the dominant stall).
     //   H >= 7 : (N >= 256) plain level loop, then recurse.
-    template <int H, int OP, int STRIDE>
+    //   COOP   : (phase 0 of a list decode, H = 5 or 6: every frame has ONE live path, in slot 0) the MP lanes of a group
+    //            share the reduction of the channel row instead of repeating it on dead slots: the lane of slot s takes the
+    //            groups g = s, s + MP, ... and writes heights H..H-3 into SLOT 0 (src must then be the frame's channel row,
+    //            the same for all lanes of the group); from height H-3 down every lane continues on its own.  Same f
+    //            operations on the same inputs, a quarter (M = 4) of the instructions and of the channel-row wavefronts.
+    template <int H, int OP, int STRIDE, bool COOP = false>
     static __device__ __forceinline__ void produce(const float* src, const uint32_t (&bw)[BW], const WM& wm, int lane,
                                                    float& a, float& b) {
         constexpr int S = 1 << H;
-        float* own = base<H>(wm) + lane;
+        static_assert(!COOP || (H >= 5 && H <= 6 && MP > 1 && OP == 0), "cooperative form: phase 0 of a list decode only");
+        const int col = COOP ? (lane & ~(MP - 1)) : lane;          // column (slot) the rows are written to
+        float* own = base<H>(wm) + col;
         if constexpr (H <= 3) {
             float v[S];
 #pragma unroll
@@ -458,9 +465,9 @@ struct Tree {
         } else if constexpr (H <= 6) {
             constexpr int G = S / 8;
             float* o0 = own + (S - 2) * 32;
-            float* o1 = base<H - 1>(wm) + lane + (S / 2 - 2) * 32;
-            float* o2 = base<H - 2>(wm) + lane + (S / 4 - 2) * 32;
-            float* o3 = base<H - 3>(wm) + lane + (S / 8 - 2) * 32;
+            float* o1 = base<H - 1>(wm) + col + (S / 2 - 2) * 32;
+            float* o2 = base<H - 2>(wm) + col + (S / 4 - 2) * 32;
+            float* o3 = base<H - 3>(wm) + col + (S / 8 - 2) * 32;
             float r0 = 0.f, r1 = 0.f;
             // one group = the 8 strided elements {g + G*k}: reduce them to heights H-1, H-2, H-3 in registers
             auto group = [&](int g, const float (&x)[8], const float (&y)[8]) {
@@ -486,14 +493,15 @@ struct Tree {
             };
             {
 #pragma unroll 1
-                for (int g = 0; g < G; ++g) {
+                for (int g = COOP ? (lane & (MP - 1)) : 0; g < G; g += COOP ? MP : 1) {
                     float x[8], y[8];
 #pragma unroll
                     for (int k = 0; k < 8; ++k) { x[k] = src[(g + G * k) * STRIDE]; y[k] = src[(g + G * k + S) * STRIDE]; }
                     group(g, x, y);
                 }
             }
-            if constexpr (H - 3 >= 2) chain_from<H - 3>(bw, wm, lane, a, b);
+            if constexpr (COOP) __syncwarp();                       // slot 0's height H-3 row is complete
+            if constexpr (H - 3 >= 2) chain_from<H - 3>(bw, wm, lane, col, a, b);
             else { a = r0; b = r1; }
         } else {
             float* dst = own + (S - 2) * 32;
@@ -512,10 +520,10 @@ struct Tree {
         }
     }
 
-    // f-chain from the own slot's height H (>= 2) down to the pair
+    // f-chain from height H (>= 2) of the slot in column `col` down to the pair (heights below H go to the own slot)
     template <int H>
-    static __device__ __forceinline__ void chain_from(const uint32_t (&bw)[BW], const WM& wm, int lane, float& a, float& b) {
-        produce<H - 1, 0, 32>(base<H>(wm) + lane + (((1 << H) - 2) * 32), bw, wm, lane, a, b);
+    static __device__ __forceinline__ void chain_from(const uint32_t (&bw)[BW], const WM& wm, int lane, int col, float& a, float& b) {
+        produce<H - 1, 0, 32>(base<H>(wm) + col + (((1 << H) - 2) * 32), bw, wm, lane, a, b);
     }
 };
 

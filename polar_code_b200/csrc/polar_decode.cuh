@@ -16,6 +16,13 @@ struct ListDecoder {
     static constexpr int XW = PathT::XW;
     static constexpr int FPW = 32 / MP;
     static constexpr uint32_t GM = (MP >= 32) ? 0xffffffffu : ((1u << MP) - 1u);
+    // Phase 0 of a list decode has one live path per frame (slot 0): instead of repeating the reduction of the channel row
+    // on the MP - 1 dead slots (10 % of all f/g work at M = 4, 12 % at M = 8), the lanes of a group split it (Tree::produce,
+    // COOP) and all paths start with their tall heights pointing at slot 0 -- the state the first fork would produce anyway.
+#ifndef PB_COOP0
+#define PB_COOP0 1
+#endif
+    static constexpr bool kCoop0 = PB_COOP0 && MP > 1;
 
     // height-1 pair (a, b) of this lane's path for the EVEN phase `phi` (lazy form of scl.py:64-82).
     // C1 = true: the caller knows phi = 2 (mod 4), i.e. only height 1 is recomputed (g of the height-2 row).
@@ -44,7 +51,14 @@ struct ListDecoder {
     if ((phi & (1 << CC)) || (phi == 0 && CC == n - 1)) {                                                             \
         if constexpr (CC < LOGMAX) {                                                                                  \
             if (CC == n - 1) {                                                                                        \
-                if (phi == 0) TreeT::template produce<CC, 0, FPW>(chanf, p.bw, wm, lane, a, b);                       \
+                if (phi == 0) {                                                                                       \
+                    if constexpr (kCoop0 && CC >= 5 && CC <= 6) {                                                     \
+                        /* one live path per frame: the group shares the row reduction, heights CC-3.. in slot 0 */   \
+                        TreeT::template produce<CC, 0, FPW, true>(chanf, p.bw, wm, lane, a, b);                       \
+                        p.P = ((uint32_t)slot * 0x11111111u) & ((1u << (4 * (CC >= 4 ? CC - 4 : 0))) - 1u);           \
+                        return;                                                                                       \
+                    } else TreeT::template produce<CC, 0, FPW>(chanf, p.bw, wm, lane, a, b);                          \
+                }                                                                                                     \
                 else TreeT::template produce<CC, 1, FPW>(chanf, p.bw, wm, lane, a, b);                                \
             } else if constexpr (CC + 1 < LOGMAX) {                                                                   \
                 const uint32_t q = (p.P >> (4 * CC)) & 0xfu;         /* slot holding height CC+1 (field CC) */        \
