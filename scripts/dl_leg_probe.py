@@ -21,6 +21,8 @@ def run(M, snr, beta, tag):
 run(4, 5.0, None, "first")
 run(4, 5.0, g["beta_M4"], "")
 run(4, 4.0, None, "")
+run(4, 4.0, g["beta_M4"], "")
+run(8, 4.0, g["beta_M8"], "")
 run(8, 5.0, g["beta_M8"], "")
 run(4, 5.0, None, "after M8")
 run(4, 6.0, None, "")
