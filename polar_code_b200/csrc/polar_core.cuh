@@ -59,11 +59,22 @@ template <int NS> __device__ __forceinline__ Code with_static_n(const Code& c) {
     return r;
 }
 
+#ifndef PB_F_XORSIGN
+#define PB_F_XORSIGN 1
+#endif
 __device__ __forceinline__ float f_op(float a, float b) {
     // polar.py:122-123 : sign(a) sign(b) min(|a|,|b|)   (exact in fp32)
+    // One instruction: min.xorsign.abs (FMNMX.XORSIGN |a|, |b|) takes the smaller magnitude and the XOR of the two sign bits --
+    // bit for bit what fminf(|a|,|b|) with the sign OR-ed in gives (three instructions), including -0 for a zero operand.
+#if PB_F_XORSIGN
+    float r;
+    asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+#else
     float mn = fminf(fabsf(a), fabsf(b));
     uint32_t s = (__float_as_uint(a) ^ __float_as_uint(b)) & 0x80000000u;
     return __uint_as_float(__float_as_uint(mn) | s);
+#endif
 }
 __device__ __forceinline__ float g_op(float a, float b, uint32_t bit) {
     // polar.py:126-127 : b + (1-2c) a
