@@ -332,11 +332,14 @@ def main() -> None:
                       "peak_at_measured_clock": props.multi_processor_count * 128 * sm_clock,
                       "frac_at_measured_clock": lane_ops / (props.multi_processor_count * 128 * sm_clock),
                       "ncu_issue_slots_busy_pct": nc["issue_slots_busy_pct"], "ncu_warp_instructions_per_frame": wipf,
+                      "ncu_l1_data_pipe_wavefronts_pct": nc.get("l1tex_data_pipe_wavefronts_pct"),
+                      "ncu_smem_wavefronts_per_frame": nc.get("smem_wavefronts_per_frame"),
                       "ncu_source": nc["file"],
                       "issue_slot_frac_live": (wipf * B / (ms_kernel * 1e-3) / (props.multi_processor_count * 4 * sm_clock)) if wipf else None,
                       "note": "SURVEY 8(d) definition (algorithmic element-ops / lane-op peak); issue_slot_frac_live = ncu "
                               "warp-instructions per frame (profiles/) x this run's frames/s / (SMs x 4 schedulers x clock) -- "
-                              "the gap between the two is per-phase list management, not idle hardware"}
+                              "the gap between the two is per-phase list management, not idle hardware; the co-limiter is the L1 / "
+                              "shared-memory data pipe (ncu_l1_data_pipe_wavefronts_pct of its peak in the same capture)"}
 
     # ---- e2e ceiling: bare pinned H2D copies of the same buffers in the same chunks on all ranks at once -------
     chunk = 1 << 16

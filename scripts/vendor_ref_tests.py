@@ -7,7 +7,7 @@ mirror package `dl_scl_polar` re-implements on the GPU.  They are TEST INFRASTRU
 imports them, they are copied unmodified (tests/ref_tests/MANIFEST.json records the SHA-256 of every source file so a
 reviewer can check that), and they run against the mirror because the repo root provides a top-level `dl_scl_polar`
 alias.  /root/reference does not exist on the GPU box and the mirror has no CPU fallback, which is why the files have
-to travel with the repo instead of being collected in place; tests/ref_tests/conftest.py (ours) marks them `gpu`.
+to travel with the repo instead of being collected in place; tests/conftest.py marks them `gpu` at collection time.
 """
 import hashlib
 import json
