@@ -109,3 +109,30 @@ def test_dlscl_through_rate_matched_input():
             & (out["tried"].cpu().numpy() == ref["tried"]).all(axis=1))
     assert not (~same & ((flags & 3) == 0)).any()
     assert (~same).sum() <= 6 and ref["n_attempts"].max() > 2
+
+
+@pytest.mark.parametrize("N,K,poly", [(128, 64, "0x1864CFB"), (64, 33, "0x107"), (32, 17, None)])
+def test_zero_and_equal_magnitude_llrs(N, K, poly):
+    """polar.py:122-123: f = sign(a) sign(b) min(|a|,|b|) with np.sign(0) = 0; the kernels' one-instruction f
+    (min.xorsign.abs) returns a signed zero there.  Rows full of exact zeros, +-equal magnitudes and coarse integer LLRs
+    (many exact metric ties): SC decisions must be identical, list decisions identical outside flagged frames, and the
+    cooperative phase 0 (N = 64, 128) sees the same rows."""
+    from polar_code_b200.engine import PolarEngine
+    rng = np.random.default_rng(N + 7)
+    A = O.construct_info_set(N, K)
+    B = 600
+    llr = rng.integers(-3, 4, (B, N)).astype(np.float32)              # values in {-3..3}: ~14 % exact zeros, many ties
+    llr[:100] *= rng.integers(0, 2, (100, N)).astype(np.float32)       # half of the entries zeroed
+    llr[100:150] = 0.0                                                 # all-zero rows
+    llr[150:200] = np.where(rng.integers(0, 2, (50, N)) > 0, 2.5, -2.5).astype(np.float32)   # equal magnitudes everywhere
+    eng = PolarEngine(N, A, poly)
+    assert np.array_equal(eng.sc_decode(llr).cpu().numpy().astype(np.int8), O.sc_decode_batch(llr.astype(np.float64), A))
+    for M in (1, 2, 4, 8):
+        ref = O.scl_decode_batch(llr.astype(np.float64), A, M, crc=poly)
+        out = eng.scl_decode(llr, M, want=("cand", "metrics", "n_cand", "best_idx", "flags"))
+        flags = out["flags"].cpu().numpy()
+        same = ((out["cand"].cpu().numpy().astype(np.int8) == ref["cand"]).all(axis=(1, 2))
+                & (out["best_idx"].cpu().numpy() == ref["best_idx"]) & (out["n_cand"].cpu().numpy() == ref["n_cand"]))
+        assert not (~same & ((flags & 1) == 0)).any(), f"N={N} M={M}: unflagged mismatch on tied / zero LLRs"
+        fin = np.isfinite(ref["metrics"]) & same[:, None]
+        np.testing.assert_allclose(out["metrics"].cpu().numpy()[fin], ref["metrics"][fin], rtol=1e-4, atol=1e-6)
