@@ -126,7 +126,7 @@ struct pb200_engine {
     uint8_t* d_stage_ok[3] = {nullptr, nullptr, nullptr};
     uint32_t* d_stage_flags[3] = {nullptr, nullptr, nullptr};
     uint16_t* d_stage_half[3] = {nullptr, nullptr, nullptr};     // binary16 ingest: rows land here and are widened into d_stage_llr
-    int64_t stage_frames = 0;
+    int64_t stage_frames = 0, stage_half_frames = 0;
     int stage_len = 0;
     // NR + DL-SCL state
     int16_t* d_rm_dst = nullptr;   // [N] de-rate-matched position -> internal index
@@ -655,20 +655,32 @@ static int decode_host_common(pb200_engine* e, const void* h_llr, int elem, int6
     // are not overlapped, so small chunks keep them short; a chunk still fills the GPU (8 192 warps of work)
     const int64_t chunk = std::min<int64_t>(B, 1 << 16);
     if (e->stage_frames < chunk || e->stage_len != in_len) {
+        // (the recorded geometry is cleared first: an allocation that fails half-way must not leave a size behind that
+        //  makes the next call skip this block and run on freed / null buffers)
+        e->stage_frames = 0; e->stage_half_frames = 0;
         for (int i = 0; i < 3; ++i) {
+            if (e->hs[i]) CUDA_TRY(cudaStreamSynchronize(e->hs[i]));
             cudaFree(e->d_stage_llr[i]); cudaFree(e->d_stage_bits[i]); cudaFree(e->d_stage_ok[i]); cudaFree(e->d_stage_flags[i]);
             cudaFree(e->d_stage_half[i]);
             e->d_stage_llr[i] = nullptr; e->d_stage_bits[i] = nullptr; e->d_stage_ok[i] = nullptr; e->d_stage_flags[i] = nullptr;
             e->d_stage_half[i] = nullptr;
             if (!e->hs[i]) CUDA_TRY(cudaStreamCreateWithFlags(&e->hs[i], cudaStreamNonBlocking));
             CUDA_TRY(cudaMalloc((void**)&e->d_stage_llr[i], (size_t)chunk * in_len * 4));
-            CUDA_TRY(cudaMalloc((void**)&e->d_stage_half[i], (size_t)chunk * in_len * 2));
             CUDA_TRY(cudaMalloc((void**)&e->d_stage_bits[i], (size_t)chunk * K));
             CUDA_TRY(cudaMalloc((void**)&e->d_stage_ok[i], (size_t)chunk));
             CUDA_TRY(cudaMalloc((void**)&e->d_stage_flags[i], (size_t)chunk * 4));
         }
         e->stage_frames = chunk;
         e->stage_len = in_len;
+    }
+    if (elem == 2 && e->stage_half_frames < e->stage_frames) {      // binary16 landing buffers: only when that ingest is used
+        e->stage_half_frames = 0;
+        for (int i = 0; i < 3; ++i) {
+            cudaFree(e->d_stage_half[i]);
+            e->d_stage_half[i] = nullptr;
+            CUDA_TRY(cudaMalloc((void**)&e->d_stage_half[i], (size_t)e->stage_frames * in_len * 2));
+        }
+        e->stage_half_frames = e->stage_frames;
     }
     int64_t done = 0;
     int slot = 0;
