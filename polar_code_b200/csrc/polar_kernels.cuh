@@ -117,8 +117,9 @@ __device__ __forceinline__ void load_force(const Code& code, const int8_t* force
     }
 }
 
-// info-mask words of the plain list decode kernels: 0 = measured best per list size (M = 4: indexed copy of the parameters,
-// M = 2 / 8: chain of selects on laundered words), 1 / 2 force one form
+// info-mask words of the plain list decode kernels: 0 = measured best (chain of selects on laundered words for every list
+// size since v19; until v18 M = 4 preferred the indexed local copy of the parameters, form 1, which costs 88 bytes of local
+// memory per thread), 1 / 2 force one form
 #ifndef PB_DECODE_UMASK
 #define PB_DECODE_UMASK 0
 #endif
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(LOGMAX <= 7 ? (MP > 1 ? PB_LIST_THREADS : 1024
         if constexpr (FORCED) load_force<XW>(code, a.force, frame, valid, fmask, fval, flags);
         PathT p;
         Dec::init(p, lane, valid);
-        Dec::template run<TRACE, false, (MP > 1 && !FORCED && !TRACE && METRIC) ? (PB_DECODE_UMASK ? PB_DECODE_UMASK : (MP == 4 ? 1 : 2)) : 0>(code, tb.info_mask, wm, p, lane, chanf, fmask, fval, flags);
+        Dec::template run<TRACE, false, (MP > 1 && !FORCED && !TRACE && METRIC) ? (PB_DECODE_UMASK ? PB_DECODE_UMASK : 2) : 0>(code, tb.info_mask, wm, p, lane, chanf, fmask, fval, flags);
 
         // u-hat = x-hat * F^{(x)n}
         uint32_t u[XW];
