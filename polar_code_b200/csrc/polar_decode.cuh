@@ -532,7 +532,13 @@ struct ListDecoder {
         int s = end_lane & (MP - 1);
         for (int jtop = code.K - 1; jtop >= jlow; jtop -= 32) {      // (jlow > 0: the trace of a jump-started decode begins there)
             unsigned long long mine = 0;                    // slots of this lane's phases, 4 bits each, earliest phase lowest
-#pragma unroll
+            // (unrolled by 4, not 32: the walk runs once per traced decode, and its 32-fold straight-line form was 6 KB of
+            //  the trace-recording kernels' instruction footprint -- DL-SCL at 4 dB +1.8 %, 5 dB +0.7 %)
+#ifndef PB_WALK_UNROLL
+#define PB_WALK_UNROLL 4
+#endif
+            constexpr int kWalkUnroll = PB_WALK_UNROLL;
+#pragma unroll kWalkUnroll
             for (int t = 0; t < 32; ++t) {
                 const int j = jtop - t;
                 if (j >= jlow) {
