@@ -164,12 +164,14 @@ static int run_sweep(pb200_engine* e, int M, SweepArgs a, cudaStream_t st) {
             auto it = e->dl_cfg.find(MP);
             if (it == e->dl_cfg.end()) {
                 int want_wpc = std::max(4, kr.wpc / 2);
-                if (const char* env = getenv("PB200_DL_WPC")) want_wpc = std::max(1, std::min(32, atoi(env)));
+                bool forced = false;
+                if (const char* env = getenv("PB200_DL_WPC")) { want_wpc = std::max(1, std::min(32, atoi(env))); forced = true; }
                 if (want_wpc < kr.wpc) {
                     const size_t wb = warp_bytes(MP, code.N, code.K, true, code.K) + acc_bytes(MP);
                     int blocks = 0;
+                    // (an explicit PB200_DL_WPC is taken even when it leaves a few warp slots of the SM unused)
                     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, round, want_wpc * 32, wb * want_wpc) == cudaSuccess &&
-                        blocks * want_wpc >= kr.wpc * kr.ctas_per_sm) {
+                        blocks > 0 && (forced || blocks * want_wpc >= kr.wpc * kr.ctas_per_sm)) {
                         kr.wpc = want_wpc; kr.ctas_per_sm = blocks; kr.smem = (int)(wb * want_wpc);
                     } else cudaGetLastError();
                 }
